@@ -1,0 +1,104 @@
+// ba_internal.h — plan layout shared by the translation units of libbatrack_ba.so (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <vector>
+
+#include "../../include/batrack_ba.h"
+
+namespace ba {
+
+constexpr int kEdgeThreads = 256;     // CTA size of the edge pass
+constexpr int kSchurThreads = 256;    // CTA size of the per-track Schur kernel
+constexpr int kSolveThreads = 1024;   // CTA size of the window Cholesky
+constexpr int kMaxWindow = 222;       // largest band window (bw + 1) the shared-memory solver holds
+
+// Device-side view of the cached topology (all pointers device memory owned by the plan).
+struct PlanView {
+  int64_t E;
+  int N, NM, m, G, n_chunks, n_units;
+  int perm_identity;
+  const int *eperm;        // [E]   original edge id of the q-th edge in track-major (stable) order
+  const int *kx;           // [m]   patch index of compact track t (== torch.unique(kk)[t])
+  const int *tptr;         // [m+1] first sorted edge of track t
+  const int *t_grp;        // [m]   group of track t
+  const int *g_t0;         // [G+1] first track of group g
+  const int *g_pat;        // [G+1] offset of group g's pattern (its degree d = g_pat[g+1]-g_pat[g])
+  const int *g_W;          // [G]   distinct poses ("slots") touched by group g
+  const long long *g_eoff; // [G+1] offset (floats) of group g's E rows: [T_g][6 W_g]
+  const int *pat_i, *pat_j;    // [sum d] raw source / target pose per pattern position
+  const int *pat_li, *pat_lj;  // [sum d] the same as group-local slots
+  const int *slot_pose;    // group g's slots (ascending pose ids) at 2*g_pat[g] .. + W_g
+  const int *slot_ptr;     // CSR over slots of the items feeding them, at 2*g_pat[g] + g .. + W_g + 1
+  const int *slot_items;   // items (position*2 + {0: via source i, 1: via target j}) at 2*g_pat[g] ..
+  const int *c_t0, *c_grp; // [n_chunks+1], [n_chunks]  edge-pass work units (track ranges)
+  const int *u_t0, *u_grp; // [n_units+1],  [n_units]   Schur work units
+};
+
+// Per-call view: problem pointers + the layout of the reduced system for this fixedp.
+struct CallView {
+  const float *poses, *patches, *monodisp, *intr, *targets, *weights, *lmbda_vec;
+  float lmbda, ep, alpha;
+  float bounds[4];
+  int fixedp, n, loss, structure_only;   // n = free poses
+  int tstride;                           // floats per targets row (2 or 3)
+  int M;                                 // 6 n
+  int ld, off;                           // S(r,c), r >= c, lives at S[r*ld + c + off]
+  int bw;                                // scalar half bandwidth (max r - c)
+  float *S, *y;                          // reduced system (this rank's partial sums)
+  float *Est;                            // E rows
+  float2 *Cw;                            // per track (C, w) sums            (ba.py:287,292)
+  float2 *Qw;                            // per track (Q, w adjusted)         (ba.py:303-311)
+  float *dX, *dZ, *L;
+  int *status;
+  float *poses_out, *patches_out;
+};
+
+}  // namespace ba
+
+struct BaPlan {
+  BaPlanInfo info;
+  ba::PlanView v;
+  int n_total_layout, bwb_layout;      // what the reduced-system layout uses (>= the local values)
+  int device;
+  // workspace
+  float *SY, *L, *Est, *dX, *dZ;
+  float2 *Cw, *Qw;
+  int *status;
+  int64_t sy_floats;                   // capacity of SY
+  int last_n, last_fixedp;             // layout of the last ba_assemble
+  // staging buffers of ba_step_host
+  void *host_stage;
+  size_t host_stage_bytes;
+  std::vector<void *> owned;           // every cudaMalloc'ed block, for ba_plan_destroy
+  // optional per-stage timing (ba_plan_enable_timing)
+  int timing;
+  cudaEvent_t ev[BA_N_STAGES + 1];
+  unsigned ev_mask;                    // which stage boundaries were recorded by the last step
+};
+
+namespace ba {
+extern std::atomic<long long> g_launches;
+int set_cuda_error(cudaError_t e, const char *what);
+void layout_for(const BaPlan *p, int fixedp, int *n, int *bw, int *ld, int *off, int64_t *s_floats);
+}  // namespace ba
+
+#define BA_CUDA(call)                                                         \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess) return ba::set_cuda_error(e_, #call);              \
+  } while (0)
+
+#define BA_MARK(pl, k, s)                                                     \
+  do {                                                                        \
+    if ((pl)->timing) { BA_CUDA(cudaEventRecord((pl)->ev[(k)], (s))); (pl)->ev_mask |= 1u << (k); } \
+  } while (0)
+
+#define BA_LAUNCH_CHECK()                                                     \
+  do {                                                                        \
+    ba::g_launches.fetch_add(1, std::memory_order_relaxed);                   \
+    cudaError_t e_ = cudaGetLastError();                                      \
+    if (e_ != cudaSuccess) return ba::set_cuda_error(e_, "kernel launch");    \
+  } while (0)

@@ -1,0 +1,511 @@
+// ba_plan.cu — topology plan: everything about a factor graph that depends only on (ii, jj, kk).
+//
+// Replaces the per-call index work of the reference (main/backend/ba.py:219 ii.max()/jj.max(),
+// :269-277 index shift + torch.unique(kk, return_inverse=True, sorted=True)) by a cached,
+// device-built structure:
+//   * edges grouped by track, stable            -> eperm, tptr, kx   (kx == unique(kk))
+//   * "pattern groups": runs of consecutive tracks whose edge lists have identical (ii, jj)
+//     sequences. In SLAM graphs every patch of a keyframe is connected to the same frames
+//     (main/batrack.py:399-410 flatmeshgrid; removals are per frame, :1023-1026,1042-1047), so a
+//     group is "all patches of one keyframe". Within a group the relative pose Gij, its adjoint and
+//     the intrinsics are per-position constants, and index traffic disappears from the edge pass.
+//   * per group: the sorted list of distinct poses it touches ("slots"), so the group's E rows and
+//     its Schur contribution are small dense objects.
+// The caller's ii/jj/kk are only read (edge indices stay bit-exact).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "ba_internal.h"
+
+namespace ba {
+
+std::atomic<long long> g_launches{0};
+static std::mutex g_err_mu;
+static std::string g_last_cuda_error;
+
+int set_cuda_error(cudaError_t e, const char *what) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_last_cuda_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  (void)cudaGetLastError();
+  return BA_ERR_CUDA;
+}
+
+// meta block written by the prep kernels
+enum { META_ERR = 0, META_MAXPOSE, META_NOTIDENT, META_DMAX, META_WMAX, META_SPAN, META_COUNT = 8 };
+
+__global__ void k_prep_keys(const int64_t *__restrict__ ii, const int64_t *__restrict__ jj,
+                            const int64_t *__restrict__ kk, int64_t E, int N, int NM,
+                            unsigned *__restrict__ key, int *__restrict__ val, unsigned *__restrict__ eij,
+                            int *__restrict__ meta) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t i = ii[e], j = jj[e], k = kk[e];
+  bool bad = i < 0 || i >= N || j < 0 || j >= N || k < 0 || k >= NM;
+  if (bad) { atomicOr(&meta[META_ERR], 1); i = j = k = 0; }
+  key[e] = (unsigned)k;
+  val[e] = (int)e;
+  eij[e] = (unsigned)i | ((unsigned)j << 16);
+  int mx = (int)(i > j ? i : j);
+  // one atomic per warp
+  for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&meta[META_MAXPOSE], mx);
+}
+
+__global__ void k_track_flags(const unsigned *__restrict__ skey, const int *__restrict__ eperm,
+                              const unsigned *__restrict__ eij, int E, int *__restrict__ tflag,
+                              unsigned *__restrict__ sij, int *__restrict__ meta) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= E) return;
+  tflag[q] = (q == 0 || skey[q] != skey[q - 1]) ? 1 : 0;
+  int e = eperm[q];
+  sij[q] = eij[e];
+  if (e != q) meta[META_NOTIDENT] = 1;
+}
+
+__global__ void k_fill_tracks(const int *__restrict__ tflag, const int *__restrict__ tinc,
+                              const unsigned *__restrict__ skey, int E, int *__restrict__ kx,
+                              int *__restrict__ tptr) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= E) return;
+  if (tflag[q]) {
+    int t = tinc[q] - 1;
+    kx[t] = (int)skey[q];
+    tptr[t] = q;
+  }
+  if (q == E - 1) tptr[tinc[q]] = E;
+}
+
+// A track starts a new pattern group unless its edge list repeats the previous track's (ii,jj) list.
+__global__ void k_group_flags(const int *__restrict__ tinc, const int *__restrict__ tptr,
+                              const unsigned *__restrict__ sij, int E, int *__restrict__ gflag,
+                              int *__restrict__ meta) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= E) return;
+  int t = tinc[q] - 1;
+  int pos = q - tptr[t];
+  int dcur = tptr[t + 1] - tptr[t];
+  if (pos == 0) atomicMax(&meta[META_DMAX], dcur);
+  if (t == 0) { if (pos == 0) gflag[0] = 1; return; }
+  int dprev = tptr[t] - tptr[t - 1];
+  if (dcur != dprev) { if (pos == 0) gflag[t] = 1; return; }
+  if (sij[q] != sij[tptr[t - 1] + pos]) gflag[t] = 1;
+}
+
+__global__ void k_fill_groups(const int *__restrict__ gflag, const int *__restrict__ ginc, int m,
+                              int *__restrict__ g_t0, int *__restrict__ t_grp) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  int g = ginc[t] - 1;
+  t_grp[t] = g;
+  if (gflag[t]) g_t0[g] = t;
+  if (t == m - 1) g_t0[g + 1] = m;
+}
+
+// Work units = pieces of at most `tc` consecutive tracks of one group.
+__global__ void k_chunk_flags(const int *__restrict__ t_grp, const int *__restrict__ g_t0, int m, int tc,
+                              int *__restrict__ cflag) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  cflag[t] = ((t - g_t0[t_grp[t]]) % tc == 0) ? 1 : 0;
+}
+__global__ void k_fill_chunks(const int *__restrict__ cflag, const int *__restrict__ cinc,
+                              const int *__restrict__ t_grp, int m, int *__restrict__ c_t0,
+                              int *__restrict__ c_grp) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  if (cflag[t]) { int c = cinc[t] - 1; c_t0[c] = t; c_grp[c] = t_grp[t]; }
+  if (t == m - 1) c_t0[cinc[t]] = m;
+}
+
+__global__ void k_group_degree(const int *__restrict__ g_t0, const int *__restrict__ tptr, int G,
+                               int *__restrict__ g_d) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > G) return;
+  g_d[g] = g < G ? tptr[g_t0[g] + 1] - tptr[g_t0[g]] : 0;
+}
+
+// One CTA per group: slots (distinct poses, ascending), local slot of every pattern position, and
+// the per-slot item lists used by the edge pass to reduce per-edge 6-vectors into E rows.
+__global__ void k_group_slots(const int *__restrict__ g_t0, const int *__restrict__ g_pat,
+                              const int *__restrict__ tptr, const unsigned *__restrict__ sij, int N,
+                              int *__restrict__ pat_i, int *__restrict__ pat_j, int *__restrict__ pat_li,
+                              int *__restrict__ pat_lj, int *__restrict__ slot_pose,
+                              int *__restrict__ slot_ptr, int *__restrict__ slot_items,
+                              int *__restrict__ g_W, long long *__restrict__ g_esz, int *__restrict__ meta) {
+  extern __shared__ unsigned sm[];
+  const int g = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int nwords = (N + 31) >> 5;
+  unsigned *bits = sm;                    // [nwords]
+  int *pre = (int *)(sm + nwords);        // [nwords + 1] exclusive popcount prefix
+  const int pat0 = g_pat[g], d = g_pat[g + 1] - pat0;
+  const int q0 = tptr[g_t0[g]];
+  const int T = g_t0[g + 1] - g_t0[g];
+
+  for (int w = tid; w < nwords; w += nt) bits[w] = 0u;
+  __syncthreads();
+  for (int p = tid; p < d; p += nt) {
+    unsigned ij = sij[q0 + p];
+    int i = ij & 0xffff, j = ij >> 16;
+    pat_i[pat0 + p] = i;
+    pat_j[pat0 + p] = j;
+    atomicOr(&bits[i >> 5], 1u << (i & 31));
+    atomicOr(&bits[j >> 5], 1u << (j & 31));
+  }
+  __syncthreads();
+  if (tid == 0) {                         // nwords <= 2048: a serial prefix is fine for a cached plan
+    int s = 0;
+    for (int w = 0; w < nwords; ++w) { pre[w] = s; s += __popc(bits[w]); }
+    pre[nwords] = s;
+  }
+  __syncthreads();
+  const int W = pre[nwords];
+  const int sbase = 2 * pat0;
+  for (int w = tid; w < nwords; w += nt) {
+    unsigned b = bits[w];
+    int s = pre[w];
+    while (b) { int bit = __ffs(b) - 1; b &= b - 1; slot_pose[sbase + s++] = (w << 5) + bit; }
+  }
+  auto slot_of = [&](int pose) { return pre[pose >> 5] + __popc(bits[pose >> 5] & ((1u << (pose & 31)) - 1u)); };
+  for (int p = tid; p < d; p += nt) {
+    unsigned ij = sij[q0 + p];
+    pat_li[pat0 + p] = slot_of(ij & 0xffff);
+    pat_lj[pat0 + p] = slot_of(ij >> 16);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // counting sort of the 2d items by slot, ascending item id inside a slot (deterministic sums)
+    int *sp = slot_ptr + sbase + g;       // [W+1]
+    for (int s = 0; s <= W; ++s) sp[s] = 0;
+    for (int p = 0; p < d; ++p) { sp[pat_li[pat0 + p] + 1]++; sp[pat_lj[pat0 + p] + 1]++; }
+    for (int s = 0; s < W; ++s) sp[s + 1] += sp[s];
+    int *it = slot_items + sbase;
+    // fill using a moving cursor kept in `it` tail-free fashion: second pass with per-slot counters
+    // stored temporarily in pre[] (no longer needed by other threads after the barrier above)
+    for (int s = 0; s < W && s <= nwords; ++s) pre[s] = 0;
+    if (W <= nwords + 1) {
+      for (int p = 0; p < d; ++p) {
+        int a = pat_li[pat0 + p]; it[sp[a] + pre[a]++] = 2 * p;
+        int b = pat_lj[pat0 + p]; it[sp[b] + pre[b]++] = 2 * p + 1;
+      }
+    } else {                              // more slots than bitmap words: quadratic but tiny
+      for (int s = 0; s < W; ++s) {
+        int c = sp[s];
+        for (int p = 0; p < d; ++p) {
+          if (pat_li[pat0 + p] == s) it[c++] = 2 * p;
+          if (pat_lj[pat0 + p] == s) it[c++] = 2 * p + 1;
+        }
+      }
+    }
+    g_W[g] = W;
+    g_esz[g] = (long long)T * 6 * W;
+    atomicMax(&meta[META_WMAX], W);
+    int lo = slot_pose[sbase], hi = slot_pose[sbase + W - 1];
+    atomicMax(&meta[META_SPAN], hi - lo);
+  }
+}
+
+__global__ void k_zero_last(long long *p, int idx) { p[idx] = 0; }
+
+// ---- small RAII helpers (host) ---------------------------------------------------------------
+struct Scratch {
+  cudaStream_t s;
+  std::vector<void *> blocks;
+  explicit Scratch(cudaStream_t st) : s(st) {}
+  ~Scratch() { for (void *b : blocks) cudaFreeAsync(b, s); }
+  template <typename T> cudaError_t get(T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMallocAsync(&q, std::max<size_t>(n, 1) * sizeof(T), s);
+    if (e == cudaSuccess) blocks.push_back(q);
+    *p = (T *)q;
+    return e;
+  }
+};
+
+template <typename T> static cudaError_t own(BaPlan *pl, T **p, size_t n) {
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (e == cudaSuccess) pl->owned.push_back(q);
+  *p = (T *)q;
+  return e;
+}
+
+static cudaError_t inclusive_sum(Scratch &sc, const int *in, int *out, int n, cudaStream_t s) {
+  size_t bytes = 0;
+  cudaError_t e = cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, n, s);
+  if (e != cudaSuccess) return e;
+  char *tmp;
+  if ((e = sc.get(&tmp, bytes)) != cudaSuccess) return e;
+  return cub::DeviceScan::InclusiveSum(tmp, bytes, in, out, n, s);
+}
+template <typename T> static cudaError_t exclusive_sum(Scratch &sc, const T *in, T *out, int n, cudaStream_t s) {
+  size_t bytes = 0;
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, s);
+  if (e != cudaSuccess) return e;
+  char *tmp;
+  if ((e = sc.get(&tmp, bytes)) != cudaSuccess) return e;
+  return cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, n, s);
+}
+
+static inline int cdiv(int64_t a, int b) { return (int)((a + b - 1) / b); }
+
+void layout_for(const BaPlan *p, int fixedp, int *n, int *bw, int *ld, int *off, int64_t *s_floats) {
+  int nn = std::max(p->n_total_layout - fixedp, 0);
+  int M = 6 * nn;
+  int b = std::min(6 * p->bwb_layout + 5, std::max(M - 1, 0));
+  if (M > 0 && b + 1 <= kMaxWindow) {     // lower band storage: S(r,c) at r*bw + c + bw
+    *ld = b; *off = b; *s_floats = (int64_t)M * (b + 1);
+  } else {                                // dense lower storage
+    b = std::max(M - 1, 0);
+    *ld = M; *off = 0; *s_floats = (int64_t)M * M;
+  }
+  *n = nn; *bw = b;
+}
+
+static int alloc_workspace(BaPlan *pl) {
+  // capacity for the smallest fixedp (0): the reduced system only shrinks as fixedp grows
+  int n, bw, ld, off; int64_t sf;
+  layout_for(pl, 0, &n, &bw, &ld, &off, &sf);
+  int64_t need = sf + 6 * (int64_t)n + 8;
+  if (need > pl->sy_floats) {
+    BA_CUDA(own(pl, &pl->SY, need));
+    BA_CUDA(own(pl, &pl->L, sf + 8));
+    BA_CUDA(own(pl, &pl->dX, 6 * (size_t)n + 8));
+    pl->sy_floats = need;
+  }
+  pl->info.banded = (ld != 6 * n) ? 1 : 0;
+  return BA_OK;
+}
+
+}  // namespace ba
+
+using namespace ba;
+
+extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_t *kk, int64_t E,
+                              int32_t N, int32_t NM, void *stream_, BaPlan **out) {
+  if (!out) return BA_ERR_ARG;
+  *out = nullptr;
+  if (!ii || !jj || !kk || E <= 0 || E >= (int64_t)1 << 31 || N <= 0 || NM <= 0) return BA_ERR_ARG;
+  if (N > 65535) return BA_ERR_TOO_MANY_POSES;
+  cudaStream_t s = (cudaStream_t)stream_;
+  int dev = 0;
+  BA_CUDA(cudaGetDevice(&dev));
+
+  BaPlan *pl = new BaPlan();
+  std::memset(&pl->info, 0, sizeof(pl->info));
+  std::memset(&pl->v, 0, sizeof(pl->v));
+  pl->device = dev;
+  pl->SY = pl->L = pl->Est = pl->dX = pl->dZ = nullptr;
+  pl->Cw = pl->Qw = nullptr;
+  pl->status = nullptr;
+  pl->sy_floats = 0;
+  pl->last_n = pl->last_fixedp = -1;
+  pl->host_stage = nullptr;
+  pl->host_stage_bytes = 0;
+  pl->timing = 0;
+  pl->ev_mask = 0;
+  for (auto &e : pl->ev) e = nullptr;
+
+  auto fail = [&](int code) { ba_plan_destroy(pl); return code; };
+#define PL_CUDA(call)                                                                      \
+  do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_cuda_error(e_, #call); return fail(BA_ERR_CUDA); } } while (0)
+#define PL_LAUNCH() do { g_launches.fetch_add(1); PL_CUDA(cudaGetLastError()); } while (0)
+
+  const int TB = 256;
+  const int nE = (int)E;
+  int hmeta[META_COUNT];
+  {
+    Scratch sc(s);
+    unsigned *key, *skey, *eij, *sij;
+    int *val, *meta, *tflag, *tinc;
+    PL_CUDA(sc.get(&key, E)); PL_CUDA(sc.get(&skey, E)); PL_CUDA(sc.get(&eij, E)); PL_CUDA(sc.get(&sij, E));
+    PL_CUDA(sc.get(&val, E)); PL_CUDA(sc.get(&meta, META_COUNT)); PL_CUDA(sc.get(&tflag, E)); PL_CUDA(sc.get(&tinc, E));
+    int *eperm;
+    PL_CUDA(own(pl, &eperm, E));
+    PL_CUDA(cudaMemsetAsync(meta, 0, META_COUNT * sizeof(int), s));
+
+    k_prep_keys<<<cdiv(E, TB), TB, 0, s>>>(ii, jj, kk, E, N, NM, key, val, eij, meta); PL_LAUNCH();
+    {
+      int end_bit = 1;
+      while (end_bit < 32 && ((int64_t)1 << end_bit) < (int64_t)NM) ++end_bit;
+      size_t bytes = 0;
+      PL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, key, skey, val, eperm, nE, 0, end_bit, s));
+      char *tmp;
+      PL_CUDA(sc.get(&tmp, bytes));
+      PL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, key, skey, val, eperm, nE, 0, end_bit, s));
+      g_launches.fetch_add(3);
+    }
+    k_track_flags<<<cdiv(E, TB), TB, 0, s>>>(skey, eperm, eij, nE, tflag, sij, meta); PL_LAUNCH();
+    PL_CUDA(inclusive_sum(sc, tflag, tinc, nE, s));
+    int m = 0;
+    PL_CUDA(cudaMemcpyAsync(&m, tinc + (nE - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaMemcpyAsync(hmeta, meta, sizeof(hmeta), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaStreamSynchronize(s));
+    if (hmeta[META_ERR]) return fail(BA_ERR_INDEX_RANGE);
+
+    int *kx, *tptr, *t_grp, *gflag, *ginc;
+    PL_CUDA(own(pl, &kx, m)); PL_CUDA(own(pl, &tptr, m + 1)); PL_CUDA(own(pl, &t_grp, m));
+    PL_CUDA(sc.get(&gflag, m)); PL_CUDA(sc.get(&ginc, m));
+    PL_CUDA(cudaMemsetAsync(gflag, 0, (size_t)m * sizeof(int), s));
+    k_fill_tracks<<<cdiv(E, TB), TB, 0, s>>>(tflag, tinc, skey, nE, kx, tptr); PL_LAUNCH();
+    k_group_flags<<<cdiv(E, TB), TB, 0, s>>>(tinc, tptr, sij, nE, gflag, meta); PL_LAUNCH();
+    PL_CUDA(inclusive_sum(sc, gflag, ginc, m, s));
+    int G = 0;
+    PL_CUDA(cudaMemcpyAsync(&G, ginc + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaStreamSynchronize(s));
+
+    int *g_t0, *g_pat, *g_W, *g_d;
+    long long *g_eoff, *g_esz;
+    PL_CUDA(own(pl, &g_t0, G + 1)); PL_CUDA(own(pl, &g_pat, G + 1)); PL_CUDA(own(pl, &g_W, G));
+    PL_CUDA(own(pl, &g_eoff, G + 1));
+    PL_CUDA(sc.get(&g_d, G + 1)); PL_CUDA(sc.get(&g_esz, G + 1));
+    k_fill_groups<<<cdiv(m, TB), TB, 0, s>>>(gflag, ginc, m, g_t0, t_grp); PL_LAUNCH();
+    k_group_degree<<<cdiv(G + 1, TB), TB, 0, s>>>(g_t0, tptr, G, g_d); PL_LAUNCH();
+    PL_CUDA(exclusive_sum(sc, g_d, g_pat, G + 1, s));
+
+    // work units: edge-pass chunks and Schur units (fewer, larger: their flush is (6W)^2 atomics)
+    const int sms = 148;
+    int tc = std::min(64, std::max(8, cdiv(m, 2 * sms)));
+    int tu = std::min(128, std::max(16, 16 * cdiv(cdiv(m, 2 * sms), 16)));
+    int *cflag, *cinc;
+    PL_CUDA(sc.get(&cflag, m)); PL_CUDA(sc.get(&cinc, m));
+    int counts[2] = {0, 0};
+    int *unit_t0[2], *unit_grp[2];
+    for (int pass = 0; pass < 2; ++pass) {
+      k_chunk_flags<<<cdiv(m, TB), TB, 0, s>>>(t_grp, g_t0, m, pass == 0 ? tc : tu, cflag); PL_LAUNCH();
+      PL_CUDA(inclusive_sum(sc, cflag, cinc, m, s));
+      PL_CUDA(cudaMemcpyAsync(&counts[pass], cinc + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+      PL_CUDA(cudaStreamSynchronize(s));
+      PL_CUDA(own(pl, &unit_t0[pass], counts[pass] + 1));
+      PL_CUDA(own(pl, &unit_grp[pass], counts[pass]));
+      k_fill_chunks<<<cdiv(m, TB), TB, 0, s>>>(cflag, cinc, t_grp, m, unit_t0[pass], unit_grp[pass]); PL_LAUNCH();
+    }
+
+    int pat_total = 0;
+    PL_CUDA(cudaMemcpyAsync(&pat_total, g_pat + G, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaStreamSynchronize(s));
+    int *pat_i, *pat_j, *pat_li, *pat_lj, *slot_pose, *slot_ptr, *slot_items;
+    PL_CUDA(own(pl, &pat_i, pat_total)); PL_CUDA(own(pl, &pat_j, pat_total));
+    PL_CUDA(own(pl, &pat_li, pat_total)); PL_CUDA(own(pl, &pat_lj, pat_total));
+    PL_CUDA(own(pl, &slot_pose, 2 * (size_t)pat_total)); PL_CUDA(own(pl, &slot_items, 2 * (size_t)pat_total));
+    PL_CUDA(own(pl, &slot_ptr, 2 * (size_t)pat_total + G + 1));
+    {
+      int nwords = (N + 31) / 32;
+      size_t smem = (size_t)(2 * nwords + 1) * sizeof(int);
+      k_group_slots<<<G, 128, smem, s>>>(g_t0, g_pat, tptr, sij, N, pat_i, pat_j, pat_li, pat_lj, slot_pose,
+                                         slot_ptr, slot_items, g_W, g_esz, meta); PL_LAUNCH();
+    }
+    k_zero_last<<<1, 1, 0, s>>>(g_esz, G); PL_LAUNCH();
+    PL_CUDA(exclusive_sum(sc, g_esz, g_eoff, G + 1, s));
+    long long esize = 0;
+    PL_CUDA(cudaMemcpyAsync(&esize, g_eoff + G, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaMemcpyAsync(hmeta, meta, sizeof(hmeta), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaStreamSynchronize(s));
+
+    PlanView &v = pl->v;
+    v.E = E; v.N = N; v.NM = NM; v.m = m; v.G = G; v.n_chunks = counts[0]; v.n_units = counts[1];
+    v.perm_identity = hmeta[META_NOTIDENT] ? 0 : 1;
+    v.eperm = eperm; v.kx = kx; v.tptr = tptr; v.t_grp = t_grp; v.g_t0 = g_t0; v.g_pat = g_pat; v.g_W = g_W;
+    v.g_eoff = g_eoff; v.pat_i = pat_i; v.pat_j = pat_j; v.pat_li = pat_li; v.pat_lj = pat_lj;
+    v.slot_pose = slot_pose; v.slot_ptr = slot_ptr; v.slot_items = slot_items;
+    v.c_t0 = unit_t0[0]; v.c_grp = unit_grp[0]; v.u_t0 = unit_t0[1]; v.u_grp = unit_grp[1];
+
+    BaPlanInfo &in = pl->info;
+    in.n_edges = E; in.n_poses = N; in.n_patches = NM; in.n_total = hmeta[META_MAXPOSE] + 1;
+    in.n_tracks = m; in.n_groups = G; in.n_chunks = counts[0]; in.max_degree = hmeta[META_DMAX];
+    in.max_slots = hmeta[META_WMAX]; in.block_bandwidth = hmeta[META_SPAN]; in.perm_identity = v.perm_identity;
+    pl->n_total_layout = in.n_total;
+    pl->bwb_layout = in.block_bandwidth;
+
+    PL_CUDA(own(pl, &pl->Est, (size_t)esize + 8));
+    PL_CUDA(own(pl, &pl->Cw, m)); PL_CUDA(own(pl, &pl->Qw, m)); PL_CUDA(own(pl, &pl->dZ, m));
+    PL_CUDA(own(pl, &pl->status, 4));
+    PL_CUDA(cudaMemsetAsync(pl->status, 0, 4 * sizeof(int), s));
+    if (alloc_workspace(pl) != BA_OK) return fail(BA_ERR_CUDA);
+    in.workspace_bytes = (int64_t)(esize + 8) * 4 + (int64_t)m * 20 + pl->sy_floats * 8;
+  }  // Scratch frees (stream-ordered)
+  PL_CUDA(cudaStreamSynchronize(s));
+#undef PL_CUDA
+#undef PL_LAUNCH
+  *out = pl;
+  return BA_OK;
+}
+
+extern "C" void ba_plan_destroy(BaPlan *pl) {
+  if (!pl) return;
+  for (void *p : pl->owned) cudaFree(p);
+  if (pl->host_stage) cudaFree(pl->host_stage);
+  for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
+  delete pl;
+}
+
+extern "C" int ba_plan_info(const BaPlan *pl, BaPlanInfo *out) {
+  if (!pl || !out) return BA_ERR_ARG;
+  *out = pl->info;
+  return BA_OK;
+}
+
+extern "C" int ba_plan_set_layout(BaPlan *pl, int32_t n_total, int32_t bwb) {
+  if (!pl || n_total < pl->info.n_total || bwb < pl->info.block_bandwidth || n_total > pl->info.n_poses)
+    return BA_ERR_ARG;
+  pl->n_total_layout = n_total;
+  pl->bwb_layout = bwb;
+  return ba::alloc_workspace(pl);
+}
+
+extern "C" int ba_plan_enable_timing(BaPlan *pl, int enable) {
+  if (!pl) return BA_ERR_ARG;
+  if (enable) for (auto &e : pl->ev) if (!e) BA_CUDA(cudaEventCreate(&e));
+  pl->timing = enable ? 1 : 0;
+  pl->ev_mask = 0;
+  return BA_OK;
+}
+
+// Stage k ran between boundary events k and k+1; stages that did not run report 0.
+extern "C" int ba_plan_last_timing(BaPlan *pl, float *ms) {
+  if (!pl || !ms || !pl->timing) return BA_ERR_ARG;
+  for (int k = BA_N_STAGES; k >= 0; --k)
+    if (pl->ev_mask & (1u << k)) { BA_CUDA(cudaEventSynchronize(pl->ev[k])); break; }
+  for (int k = 0; k < BA_N_STAGES; ++k) {
+    ms[k] = 0.0f;
+    if (!(pl->ev_mask & (1u << k))) continue;
+    int nxt = k + 1;
+    while (nxt <= BA_N_STAGES && !(pl->ev_mask & (1u << nxt))) ++nxt;
+    if (nxt > BA_N_STAGES) continue;
+    // a boundary only opens a stage if that stage actually launched something: see ba_kernels.cu
+    BA_CUDA(cudaEventElapsedTime(&ms[k], pl->ev[k], pl->ev[nxt]));
+  }
+  return BA_OK;
+}
+
+extern "C" int ba_plan_tracks(const BaPlan *pl, int32_t *kx_out, void *stream) {
+  if (!pl || !kx_out) return BA_ERR_ARG;
+  BA_CUDA(cudaMemcpyAsync(kx_out, pl->v.kx, (size_t)pl->v.m * sizeof(int), cudaMemcpyDeviceToDevice,
+                          (cudaStream_t)stream));
+  return BA_OK;
+}
+
+extern "C" const char *ba_error_string(int code) {
+  switch (code) {
+    case BA_OK: return "ok";
+    case BA_ERR_CUDA: return "CUDA runtime error (see ba_last_cuda_error)";
+    case BA_ERR_ARG: return "invalid argument";
+    case BA_ERR_INDEX_RANGE: return "edge index out of range";
+    case BA_ERR_TOO_MANY_POSES: return "pose buffer longer than 65535";
+    case BA_ERR_NO_DEVICE: return "no usable sm_100 CUDA device";
+    default: return "unknown error";
+  }
+}
+extern "C" const char *ba_last_cuda_error(void) {
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(ba::g_err_mu);
+  copy = ba::g_last_cuda_error;
+  return copy.c_str();
+}
+extern "C" int ba_version(void) { return 100; }
+extern "C" int64_t ba_launch_count(void) { return (int64_t)ba::g_launches.load(); }

@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — BA iterations/sec on the synthetic 256-keyframe / 65 536-track / 1 245 184-edge graph
+(BASELINE.json configs[2]), one step = one BA_rgbd_droid(structure_only=False) call.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    torchrun ... bench.py --gpus N ...                       # keyframe-sharded, one NCCL all-reduce of [S|y] per step
+    python bench.py --impl reference ...                     # the reference algorithm on the host CPU cores
+
+Prints ONE JSON line (rank 0). See DESIGN.md §Measurement for what every field means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "BA iterations/sec (256 KF, 64k tracks)"
+WORKLOAD = "cfg3: synthetic 256-KF / 65536-track / 1245184-edge graph, BA_rgbd_droid(structure_only=False), " \
+           "huber, ep=10, lmbda=1e-4, alpha=0.05, fixedp=1, state chained over iterations and reset every 10"
+LM_ITERS = 10
+
+
+def algorithmic_bytes(prob_full, n_free):
+    """SURVEY.md §8(d) / BASELINE.md §3: 40 B per edge (3 int64 indices + target + weight) + per-iteration
+    state (reads 44 B/keyframe + 16 B/track, writes 144 n^2 + 24 n + 8 m, outputs 28 B/keyframe + 4 B/track)."""
+    E, N = prob_full.E, prob_full.poses.shape[0]
+    m = int(np.unique(prob_full.kk).shape[0])
+    return 40 * E + 44 * N + 16 * m + 144 * n_free * n_free + 24 * n_free + 8 * m + 28 * N + 4 * m
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the GPU is under the bench load."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device_index):
+        self.rows, self.proc, self.t0 = [], None, time.time()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            sel = "GPU-" + uuid if not uuid.startswith("GPU-") else uuid
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", sel, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        inside = [r for t, r in self.rows if any(a <= t <= b for a, b in windows)] or [r for _, r in self.rows]
+        sm = [float(r[0]) for r in inside if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in inside for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        pw = [float(r[2]) for r in inside if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(inside), "power_w_max": max(pw) if pw else None}
+
+
+def run_reference(args, rank):
+    """The reference's algorithm on the host cores: oracle/ba_oracle.py mode="dense" (the restatement of
+    main/backend/ba.py + projective_ops.py with the dense E and the dense Schur GEMM the reference uses),
+    fp32, all host threads. kind="port": the reference's own extension cannot be built here (Eigen 3.4.0 is
+    not vendored) and /root/reference does not exist on the GPU box."""
+    if rank != 0:
+        return
+    from batrack_b200 import synth
+    from oracle import ba_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    prob = synth.make_config("cfg3")
+    f = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float()
+    g = lambda a: torch.from_numpy(np.ascontiguousarray(a)).long()
+    st = dict(poses=f(prob.poses), xyd=f(prob.patches))
+    mono, intr, tg, w = f(prob.monodisp), f(prob.intrinsics), f(prob.targets), f(prob.weights)
+    ii, jj, kk = g(prob.ii), g(prob.jj), g(prob.kk)
+
+    def step(k):
+        if k % LM_ITERS == 0:
+            st["poses"], st["xyd"] = f(prob.poses), f(prob.patches)
+        poses, disp = ba_oracle.ba_step(st["poses"], st["xyd"], mono, intr, tg, w, prob.lmbda, ii, jj, kk, prob.bounds,
+                                        ep=prob.ep, fixedp=prob.fixedp, structure_only=False, loss=prob.loss,
+                                        alpha=prob.alpha, mode="dense")
+        st["poses"], st["xyd"] = poses, torch.cat([st["xyd"][:, :2], disp[:, None]], 1)
+
+    t0 = time.perf_counter()
+    step(0)
+    t_one = time.perf_counter() - t0
+    budget = 150.0
+    warm = max(0, min(args.warmup, int(20.0 / max(t_one, 1e-3)))) if args.warmup > 0 else 0
+    for k in range(max(warm - 1, 0)):
+        step(k + 1)
+    steps = max(1, min(args.steps, int(budget / max(t_one, 1e-3))))
+    t0 = time.perf_counter()
+    for k in range(steps):
+        step(k)
+    dt = time.perf_counter() - t0
+    val = steps / dt
+    sample = f"{steps} full cfg3 BA calls (1245184 edges each), dense E + dense Schur GEMM as the reference does"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "it/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": val, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline(prob, budget_s=25.0):
+    from oracle import ba_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    f = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float()
+    g = lambda a: torch.from_numpy(np.ascontiguousarray(a)).long()
+    a = (f(prob.poses), f(prob.patches), f(prob.monodisp), f(prob.intrinsics), f(prob.targets), f(prob.weights), prob.lmbda,
+         g(prob.ii), g(prob.jj), g(prob.kk), prob.bounds)
+    kw = dict(ep=prob.ep, fixedp=prob.fixedp, structure_only=False, loss=prob.loss, alpha=prob.alpha, mode="dense")
+    t0 = time.perf_counter()
+    ba_oracle.ba_step(*a, **kw)                       # warm-up
+    t_one = time.perf_counter() - t0
+    reps = max(1, min(3, int(budget_s / max(t_one, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ba_oracle.ba_step(*a, **kw)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": 1.0 / dt, "unit": "it/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} full cfg3 BA calls after 1 warm-up, oracle/ba_oracle.py mode=dense fp32 ({dt:.2f} s/call)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    from batrack_b200 import _capi, synth
+    from batrack_b200.ba import BA_rgbd_droid
+    from batrack_b200.lietorch import SE3
+    from batrack_b200.plan import Plan
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    group = dist.group.WORLD if world > 1 else None
+
+    n_kf = synth.CONFIGS["cfg3"][0]
+    lo, hi = (n_kf * rank) // world, (n_kf * (rank + 1)) // world
+    prob = synth.make_config("cfg3", kf_lo=lo, kf_hi=hi)
+    E_local, N, NM = prob.E, prob.poses.shape[0], prob.patches.shape[0]
+
+    # pinned host copies (e2e) and device-resident copies (value)
+    host = {k: v.pin_memory() for k, v in prob.as_torch().items()}
+    d = {k: v.to(dev) for k, v in host.items()}
+    plan = Plan(d["ii"], d["jj"], d["kk"], N, NM)
+    n_total, bwb = plan.info.n_total, plan.info.block_bandwidth
+    if world > 1:
+        lay = torch.tensor([n_total, bwb], device=dev)
+        dist.all_reduce(lay, op=dist.ReduceOp.MAX)
+        n_total, bwb = int(lay[0]), int(lay[1])
+        plan.set_layout(n_total, bwb)
+    n_free = n_total - prob.fixedp
+
+    def ba(poses, patches, src):
+        return BA_rgbd_droid(poses, patches, src["patches_monodisp"], src["intrinsics"], src["targets_2d"], None,
+                             src["weights"], prob.lmbda, d["ii"], d["jj"], d["kk"], prob.bounds, ep=prob.ep,
+                             fixedp=prob.fixedp, structure_only=False, loss=prob.loss, alpha=prob.alpha,
+                             group=group, plan=plan)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    state = {}
+
+    def step(k):
+        if k % LM_ITERS == 0:
+            state["G"], state["p"] = SE3(d["poses"]), d["patches"]
+        state["G"], state["p"] = ba(state["G"], state["p"], d)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    windows = []
+
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+
+    # ---- value: device-resident inputs, per-step CUDA events, L2 flushed between steps ----
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = _capi.launch_count()
+    w0 = time.time()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        step(k)
+        ev[k][1].record()
+    barrier()
+    windows.append((w0, time.time()))
+    launches = _capi.launch_count() - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t[0])
+    ms_per_step = total_ms / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- per-kernel durations (CUDA events recorded by the library on the launch stream) ----
+    plan.enable_timing(True)
+    stages = {}
+    n_prof = min(args.steps, 50)
+    for k in range(n_prof):
+        flush.zero_()
+        step(k)
+        for name, ms in plan.last_timing().items():
+            stages[name] = stages.get(name, 0.0) + ms / n_prof
+    plan.enable_timing(False)
+    barrier()
+
+    # ---- e2e: host (pinned) buffers in, host buffers out, copies inside the timed region ----
+    h2d_keys = ("poses", "patches", "patches_monodisp", "intrinsics", "targets_2d", "weights")
+    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in h2d_keys)
+    out_pose = torch.empty((1, N, 7), dtype=torch.float32).pin_memory()
+    out_patch = torch.empty((1, NM, 3, 1, 1), dtype=torch.float32).pin_memory()
+    d2h_bytes = out_pose.numel() * 4 + out_patch.numel() * 4
+
+    def e2e_step():
+        src = {k: host[k].to(dev, non_blocking=True) for k in h2d_keys}
+        G, p = ba(SE3(src["poses"]), src["patches"], src)
+        out_pose.copy_(G.data, non_blocking=True)
+        out_patch.copy_(p, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    n_e2e = min(args.steps, 100)
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_e2e)]
+    w0 = time.time()
+    for k in range(n_e2e):
+        flush.zero_()
+        ev2[k][0].record()
+        e2e_step()
+        ev2[k][1].record()
+    barrier()
+    windows.append((w0, time.time()))
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t[0])
+    e2e_val = 1e3 * n_e2e / e2e_ms
+
+    # ---- cold call: index upload + topology plan + one step (what the first call on a new graph costs) ----
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    idx = [host[k].to(dev, non_blocking=True) for k in ("ii", "jj", "kk")]
+    cold_plan = Plan(*idx, N, NM)
+    torch.cuda.synchronize()
+    plan_ms = 1e3 * (time.perf_counter() - t0)
+    del cold_plan
+
+    # ---- keep the same load running long enough for nvidia-smi to see it ----
+    if sampler is not None or world > 1:
+        w0 = time.time()
+        reps = int(min(4000, max(50, 1.2e3 / max(ms_per_step, 1e-3))))
+        for k in range(reps):
+            step(k)
+        barrier()
+        windows.append((w0, time.time()))
+    clocks = sampler.stop(windows) if sampler is not None else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    full = synth.make_config("cfg3") if world > 1 else prob
+    alg = algorithmic_bytes(full, n_free)
+    edge_ms = stages.get("edge_pass", 0.0)
+    alg_rank = alg / world                       # each rank streams its shard of the edges
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    except Exception:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_rank / (edge_ms * 1e-3) / 1e9 if edge_ms > 0 else None
+    tot = sum(stages.values()) or 1.0
+    out = {
+        "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "keyframes": n_kf, "tracks": int(np.unique(full.kk).shape[0]), "edges": full.E,
+                   "free_poses": n_free, "sharding": f"keyframe windows over {world} rank(s), one NCCL all-reduce of [S|y] per step"
+                   if world > 1 else "none", "l2": "256 MiB buffer written between timed steps",
+                   "reduced_system": "band" if plan.info.banded else "dense", "block_bandwidth": bwb,
+                   "plan": {"groups": plan.info.n_groups, "chunks": plan.info.n_chunks, "perm_identity": plan.info.perm_identity,
+                            "build_ms_cold": plan_ms}},
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "steps": n_e2e, "note": "pinned host float inputs -> device -> BA_rgbd_droid -> pinned host outputs per step; "
+                "ii/jj/kk and the topology plan stay resident (they change only when the SLAM graph changes)"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_edge_pass (residual + Jacobian + per-track reduction)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                     "traffic": None, "algorithmic_bytes": alg_rank, "kernel_ms": edge_ms, "peak_source": peak_src},
+        "kernels": {k: {"ms": v, "share": v / tot} for k, v in stages.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(prob)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

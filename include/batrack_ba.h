@@ -1,0 +1,179 @@
+/* batrack_ba.h — C ABI of the B200-native bundle-adjustment backend (libbatrack_ba.so).
+ *
+ * Drop-in boundary for BA-Track's sparse-SLAM hot path. Every entry point names the reference
+ * interface it replaces (paths relative to the reference repo root):
+ *
+ *   ba_plan_*        the per-call index preparation of main/backend/ba.py:219,269-277
+ *                    (ii.max()/jj.max(), index shift, torch.unique(kk)) — hoisted out of the
+ *                    iteration and cached per graph topology
+ *   ba_step          one call of BA_rgbd_droid (main/backend/ba.py:217-339) or BA (:103-213)
+ *   ba_assemble /    the same call split at the point where a keyframe-sharded graph exchanges the
+ *   ba_solve_update  reduced camera system: ba.py:223-322 | ba.py:323-337
+ *   ba_reproject     pops.transform(..., jacobian=False) (main/backend/projective_ops.py:54-70,102-105)
+ *   se3_*            the SE3 forward entry points of the lietorch_backends extension
+ *                    (main/backend/lietorch/src/lietorch.cpp:18,69,97,155,214,286-316)
+ *
+ * Conventions: all array arguments are DEVICE pointers unless a name ends in _host; float32 values,
+ * int64 indices exactly as the reference's caller holds them (main/batrack.py:864-875); every launch
+ * goes to the caller's stream (`stream` is a cudaStream_t passed as void*); nothing synchronises the
+ * host except ba_plan_create (once per topology) and the *_host helpers. Inputs are never modified.
+ * Return value: 0 on success, a negative BA_ERR_* code otherwise (ba_error_string() explains it).
+ * Numerical failure is NOT an error, exactly like the reference: a failed Cholesky leaves the poses
+ * unchanged (ba.py:9-13), NaNs in the pose update trigger one retry with lm = 1e-3 (ba.py:324-325).
+ */
+#ifndef BATRACK_BA_H
+#define BATRACK_BA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BA_OK 0
+#define BA_ERR_CUDA (-1)          /* a CUDA runtime call failed (see ba_last_cuda_error) */
+#define BA_ERR_ARG (-2)           /* null pointer / negative size / unsupported value */
+#define BA_ERR_INDEX_RANGE (-3)   /* an edge index is outside [0,N) / [0,NM) */
+#define BA_ERR_TOO_MANY_POSES (-4)/* N > 65535 (pose indices are packed to 16 bits) */
+#define BA_ERR_NO_DEVICE (-5)     /* no sm_100 device / kernel image not loadable */
+
+#define BA_LOSS_TRIVIAL 0         /* compute_kernel_weight, main/backend/ba.py:81-100 */
+#define BA_LOSS_HUBER 1
+#define BA_LOSS_CAUCHY 2
+
+typedef struct BaPlan BaPlan;     /* opaque: cached topology + per-iteration workspace */
+
+/* What ba_plan_create learned about the graph (host-side copy). */
+typedef struct {
+  int64_t n_edges;       /* E */
+  int32_t n_poses;       /* N: length of the pose buffer */
+  int32_t n_patches;     /* NM: length of the patch buffer */
+  int32_t n_total;       /* max(ii.max(), jj.max()) + 1          (ba.py:219) */
+  int32_t n_tracks;      /* m = len(unique(kk))                  (ba.py:276-277) */
+  int32_t n_groups;      /* runs of consecutive tracks sharing one (ii,jj) edge pattern */
+  int32_t n_chunks;      /* CTA work units of the edge pass */
+  int32_t max_degree;    /* longest track (edges) */
+  int32_t max_slots;     /* most distinct poses touched by one group */
+  int32_t block_bandwidth; /* max |pose_a - pose_b| over poses coupled by one group */
+  int32_t perm_identity; /* 1 if the caller's edge order is already track-major */
+  int32_t banded;        /* 1 if the reduced system is stored/solved in band form */
+  int64_t workspace_bytes;
+} BaPlanInfo;
+
+/* One BA call. Field comments give the reference argument (ba.py:217) and its torch shape. */
+typedef struct {
+  const float *poses;        /* poses.data        [1,N,7]  tx ty tz qx qy qz qw */
+  const float *patches;      /* patches           [1,NM,3,1,1]  x y inverse-depth (P = 1) */
+  const float *monodisp;     /* patches_monodisp  [1,NM,1]; NULL selects BA (ba.py:103) */
+  const float *intrinsics;   /* intrinsics        [1,N,4]  fx fy cx cy */
+  const float *targets;      /* targets_2d        [1,E,2] */
+  const float *weights;      /* weights           [1,E,2] */
+  const float *lmbda_vec;    /* lmbda as a tensor of m values (ba.py:299-300) or NULL */
+  float lmbda;               /* lmbda as a python float (used when lmbda_vec == NULL) */
+  float ep;                  /* ep */
+  float alpha;               /* alpha */
+  float bounds[4];           /* bounds [x0,y0,x1,y1] */
+  int32_t fixedp;            /* fixedp */
+  int32_t structure_only;    /* structure_only */
+  int32_t loss;              /* BA_LOSS_* */
+  int32_t targets_stride;    /* floats between consecutive targets rows: 2, or 3 when the caller passes the
+                                view targets_3d[...,:2] (main/batrack.py:871); 0 means 2 */
+  float *poses_out;          /* returned poses.data [1,N,7] (fresh buffer; may NOT alias poses) */
+  float *patches_out;        /* returned patches    [1,NM,3,1,1] (fresh buffer) */
+} BaProblem;
+
+/* ---- topology plan ------------------------------------------------------------------------- */
+
+/* Builds the cached topology for (ii,jj,kk) [E] int64 device arrays: validates ranges, groups the
+ * edges by track (stable), compacts kk -> [0,m) like torch.unique(sorted=True), finds pattern
+ * groups / chunks, and allocates the workspace. Synchronises `stream`. */
+int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_t *kk, int64_t n_edges,
+                   int32_t n_poses, int32_t n_patches, void *stream, BaPlan **out);
+void ba_plan_destroy(BaPlan *plan);
+int ba_plan_info(const BaPlan *plan, BaPlanInfo *out);
+
+/* Sharded graphs: make n_total / block_bandwidth agree across ranks so that every
+ * rank lays the reduced camera system out identically. Pass the max over ranks. */
+int ba_plan_set_layout(BaPlan *plan, int32_t n_total, int32_t block_bandwidth);
+
+/* Device copy-outs for tests and callers that need the compacted indices (ba.py:276): kx[m] int32
+ * patch index of every compact track, sorted ascending. */
+int ba_plan_tracks(const BaPlan *plan, int32_t *kx_out /* device, m ints */, void *stream);
+
+/* ---- the iteration ------------------------------------------------------------------------- */
+
+/* One full BA call on one device: assemble -> Schur -> solve -> back-substitute -> retract. */
+int ba_step(BaPlan *plan, const BaProblem *prob, void *stream);
+
+/* First half: residuals, Jacobians, per-track Schur complement. Leaves the (partial) reduced camera
+ * system in the plan's exchange buffer [S | y] (see ba_plan_reduced_system). No-op for
+ * structure-only calls apart from the per-track C, w. */
+int ba_assemble(BaPlan *plan, const BaProblem *prob, void *stream);
+
+/* The exchange buffer: `n_floats` contiguous floats holding the lower (band) storage of S followed
+ * by y. A sharded caller all-reduces (sum) exactly this range between ba_assemble and
+ * ba_solve_update. Valid for the fixedp of the last ba_assemble. */
+int ba_plan_reduced_system(const BaPlan *plan, float **ptr, int64_t *n_floats);
+
+/* Second half: damped Cholesky solve of the reduced system, depth back-substitution, retractions. */
+int ba_solve_update(BaPlan *plan, const BaProblem *prob, void *stream);
+
+/* Debug/test view of the last reduced system: writes dense row-major S [6n,6n] (symmetrised),
+ * y [6n], dX [6n], per-track C_damped^-1 = Q [m], w [m], dZ [m] (any pointer may be NULL). */
+int ba_plan_debug_dense(const BaPlan *plan, int32_t n, float *S, float *y, float *dX, float *Q,
+                        float *w, float *dZ, void *stream);
+
+/* Solver status of the last ba_solve_update: bit0 = Cholesky failed (dX = 0), bit1 = NaN retry
+ * with lm = 1e-3 taken, bit2 = retry failed as well. Device int; copy when needed. */
+int ba_plan_status_ptr(const BaPlan *plan, int32_t **dev_status);
+
+/* Per-kernel device timing of the last ba_step / ba_assemble + ba_solve_update (bench.py's roofline):
+ * when enabled, CUDA events are recorded on the launch stream between the stages; ba_plan_last_timing
+ * waits for the last event and writes BA_N_STAGES durations in milliseconds. */
+#define BA_STAGE_ZERO 0      /* memset of the reduced system */
+#define BA_STAGE_EDGE 1      /* edge pass: residuals + Jacobians + per-track reduction (the HBM-bound kernel) */
+#define BA_STAGE_TRACKQ 2    /* per-track damping / prior */
+#define BA_STAGE_SCHUR 3     /* per-track Schur complement */
+#define BA_STAGE_SOLVE 4     /* damped Cholesky solve of the reduced camera system */
+#define BA_STAGE_BACKSUB 5   /* depth back-substitution + disparity retraction */
+#define BA_STAGE_RETR 6      /* pose retraction */
+#define BA_N_STAGES 7
+int ba_plan_enable_timing(BaPlan *plan, int enable);
+int ba_plan_last_timing(BaPlan *plan, float *ms_out /* host, BA_N_STAGES floats */);
+
+/* Host-buffer convenience for end-to-end timing: pinned or pageable HOST arrays in, results out;
+ * H2D/D2H copies are issued on `stream` and the call returns after synchronising it. */
+int ba_step_host(BaPlan *plan, const BaProblem *prob_host, void *stream);
+
+/* ---- reprojection without Jacobians --------------------------------------------------------- */
+/* coords[e] = pixel of patch kk[e] (seen in ii[e]) in frame jj[e]; valid[e] = Z > 0.2 (may be NULL).
+ * tonly != 0 drops the rotation of Gij (projective_ops.py:63-64). */
+int ba_reproject(const float *poses, const float *patches, const float *intrinsics,
+                 const int64_t *ii, const int64_t *jj, const int64_t *kk, int64_t n_edges,
+                 int32_t n_poses, int32_t n_patches, int32_t tonly, float *coords, float *valid,
+                 void *stream);
+
+/* ---- SE3 forward ops (lietorch_backends, group id 3) ---------------------------------------- */
+/* All arrays contiguous [B,7] / [B,6] / [B,4] float32 device buffers. */
+int se3_expm(const float *a, float *X, int64_t B, void *stream);                  /* lietorch.cpp:18 */
+int se3_logm(const float *X, float *a, int64_t B, void *stream);                  /* lietorch.cpp:43 */
+int se3_inv(const float *X, float *Y, int64_t B, void *stream);                   /* lietorch.cpp:69 */
+int se3_mul(const float *X, const float *Y, float *Z, int64_t B, void *stream);   /* lietorch.cpp:97 */
+int se3_adj(const float *X, const float *a, float *b, int64_t B, void *stream);   /* lietorch.cpp:126 */
+int se3_adjT(const float *X, const float *a, float *b, int64_t B, void *stream);  /* lietorch.cpp:155 */
+int se3_act(const float *X, const float *p, float *q, int64_t B, void *stream);   /* lietorch.cpp:185 */
+int se3_act4(const float *X, const float *p, float *q, int64_t B, void *stream);  /* lietorch.cpp:214 */
+int se3_as_matrix(const float *X, float *T, int64_t B, void *stream);             /* lietorch.cpp:258 */
+
+/* ---- misc ----------------------------------------------------------------------------------- */
+const char *ba_error_string(int code);
+const char *ba_last_cuda_error(void);
+int ba_version(void);
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+int64_t ba_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BATRACK_BA_H */
