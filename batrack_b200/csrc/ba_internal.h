@@ -13,7 +13,7 @@ namespace ba {
 constexpr int kEdgeThreads = 256;     // CTA size of the edge pass
 constexpr int kSchurThreads = 256;    // CTA size of the per-track Schur kernel
 constexpr int kSolveThreads = 1024;   // CTA size of the window Cholesky
-constexpr int kMaxWindow = 222;       // largest band window (bw + 1) the shared-memory solver holds
+constexpr int kMaxWindow = 150;       // largest band window (bw + 1) the shared-memory solver holds (fp64)
 
 // Device-side view of the cached topology (all pointers device memory owned by the plan).
 struct PlanView {
@@ -47,11 +47,12 @@ struct CallView {
   int M;                                 // 6 n
   int ld, off;                           // S(r,c), r >= c, lives at S[r*ld + c + off]
   int bw;                                // scalar half bandwidth (max r - c)
-  float *S, *y;                          // reduced system (this rank's partial sums)
+  double *S, *y;                         // reduced system (this rank's partial sums), fp64 accumulators
   float *Est;                            // E rows
   float2 *Cw;                            // per track (C, w) sums            (ba.py:287,292)
   float2 *Qw;                            // per track (Q, w adjusted)         (ba.py:303-311)
-  float *dX, *dZ, *L;
+  double *dX, *L;                        // pose update and Cholesky factor, fp64
+  float *dZ;
   int *status;
   float *poses_out, *patches_out;
 };
@@ -64,10 +65,11 @@ struct BaPlan {
   int n_total_layout, bwb_layout;      // what the reduced-system layout uses (>= the local values)
   int device;
   // workspace
-  float *SY, *L, *Est, *dX, *dZ;
+  double *SY, *L, *dX;
+  float *Est, *dZ;
   float2 *Cw, *Qw;
   int *status;
-  int64_t sy_floats;                   // capacity of SY
+  int64_t sy_floats;                   // capacity of SY (elements)
   int last_n, last_fixedp;             // layout of the last ba_assemble
   // staging buffers of ba_step_host
   void *host_stage;

@@ -8,13 +8,28 @@
 
 namespace ba {
 
-__device__ __forceinline__ void red_add(float *addr, float v) { atomicAdd(addr, v); }
+// Reduced-system accumulators are fp64: the per-edge math is fp32 like the reference's, but every sum
+// that feeds the (ill-conditioned) reduced solve is carried in double — see DESIGN.md §Precision.
+__device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
+
+// Ad(X)^T applied in double (R, t are the fp32 pair constants)
+__device__ __forceinline__ void adjT_apply_d(const float *R, Vec3 t, const double *a, double *b) {
+  const double tx = t.x, ty = t.y, tz = t.z;
+  const double cx = ty * a[2] - tz * a[1], cy = tz * a[0] - tx * a[2], cz = tx * a[1] - ty * a[0];
+  const double u0 = a[3] - cx, u1 = a[4] - cy, u2 = a[5] - cz;
+  b[0] = (double)R[0] * a[0] + (double)R[3] * a[1] + (double)R[6] * a[2];
+  b[1] = (double)R[1] * a[0] + (double)R[4] * a[1] + (double)R[7] * a[2];
+  b[2] = (double)R[2] * a[0] + (double)R[5] * a[1] + (double)R[8] * a[2];
+  b[3] = (double)R[0] * u0 + (double)R[3] * u1 + (double)R[6] * u2;
+  b[4] = (double)R[1] * u0 + (double)R[4] * u1 + (double)R[7] * u2;
+  b[5] = (double)R[2] * u0 + (double)R[5] * u1 + (double)R[8] * u2;
+}
 
 __device__ __forceinline__ bool pose_free(int pose, const CallView &c) {
   int a = pose - c.fixedp;          // ba.py:272-274 index shift; :33-39 range mask
   return a >= 0 && a < c.n;
 }
-__device__ __forceinline__ float *S_at(const CallView &c, int r, int col) {
+__device__ __forceinline__ double *S_at(const CallView &c, int r, int col) {
   return c.S + (size_t)r * c.ld + col + c.off;
 }
 
@@ -32,7 +47,7 @@ __device__ __forceinline__ float *S_at(const CallView &c, int r, int col) {
 constexpr int kAccComps = 27;     // Bjj lower[21] vj[6]
 
 template <bool STRUCT_ONLY>
-__global__ void __launch_bounds__(kEdgeThreads) k_edge_pass(PlanView pv, CallView cv) {
+__global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, CallView cv) {
   constexpr int NT = kEdgeThreads;
   __shared__ float sh[kAccComps * NT];      // staging (14*NT) during passes, accumulators (27*NT) at flush
   const int tau = threadIdx.x;
@@ -134,15 +149,15 @@ __global__ void __launch_bounds__(kEdgeThreads) k_edge_pass(PlanView pv, CallVie
       for (int k = 0; k < kAccComps; ++k) sh[k * NT + tau] = active ? acc[k] : 0.0f;
       __syncthreads();
       if (tau < dc) {
-        float Bl[21], vj[6];
+        double Bl[21], vj[6];
 #pragma unroll
-        for (int k = 0; k < 21; ++k) { float s = 0.0f; for (int kp = 0; kp < Tp; ++kp) s += sh[k * NT + kp * dc + tau]; Bl[k] = s; }
+        for (int k = 0; k < 21; ++k) { double s = 0.0; for (int kp = 0; kp < Tp; ++kp) s += (double)sh[k * NT + kp * dc + tau]; Bl[k] = s; }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { float s = 0.0f; for (int kp = 0; kp < Tp; ++kp) s += sh[(21 + k) * NT + kp * dc + tau]; vj[k] = s; }
+        for (int k = 0; k < 6; ++k) { double s = 0.0; for (int kp = 0; kp < Tp; ++kp) s += (double)sh[(21 + k) * NT + kp * dc + tau]; vj[k] = s; }
         const int pi = pv.pat_i[pat0 + p0 + tau], pj = pv.pat_j[pat0 + p0 + tau];
         const bool fi = pose_free(pi, cv), fj = pose_free(pj, cv);
         const int ri = 6 * (pi - cv.fixedp), rj = 6 * (pj - cv.fixedp);
-        // this thread's pair constants are those of position p0+tau only when kappa == 0 (tau < dc) — true here
+        // tau < dc means kappa == 0, so this thread's pair constants `pc` are those of position p0 + tau
         if (fj) {
 #pragma unroll
           for (int a = 0; a < 6; ++a) {
@@ -152,23 +167,23 @@ __global__ void __launch_bounds__(kEdgeThreads) k_edge_pass(PlanView pv, CallVie
           }
         }
         if (fi) {
-          float AB[6][6];                      // A * Bjj   (column c of Bjj is its row c)
+          double AB[6][6];                     // A * Bjj   (column c of Bjj is its row c)
 #pragma unroll
           for (int c = 0; c < 6; ++c) {
-            float col[6], out[6];
+            double col[6], out[6];
 #pragma unroll
             for (int a = 0; a < 6; ++a) col[a] = a >= c ? Bl[tri(a, c)] : Bl[tri(c, a)];
-            adjT_apply(pc.R, pc.t, col, out);
+            adjT_apply_d(pc.R, pc.t, col, out);
 #pragma unroll
             for (int a = 0; a < 6; ++a) AB[a][c] = out[a];
           }
-          float vi[6];
-          adjT_apply(pc.R, pc.t, vj, vi);
+          double vi[6];
+          adjT_apply_d(pc.R, pc.t, vj, vi);
 #pragma unroll
           for (int a = 0; a < 6; ++a) {
             red_add(cv.y + ri + a, -vi[a]);                                  // vi = -A vj, ba.py:289
-            float row[6];
-            adjT_apply(pc.R, pc.t, AB[a], row);                              // Bii = (A Bjj) A^T, ba.py:279
+            double row[6];
+            adjT_apply_d(pc.R, pc.t, AB[a], row);                            // Bii = (A Bjj) A^T, ba.py:279
 #pragma unroll
             for (int b = 0; b <= a; ++b) red_add(S_at(cv, ri + a, ri + b), row[b]);
           }
@@ -222,9 +237,12 @@ __global__ void k_track_q(PlanView pv, CallView cv) {
 // =================================================================================================
 // K2  per-track Schur complement (ba.py:311-322):  S -= sum_k Q_k E_k E_k^T,  y -= sum_k Q_k w_k E_k
 //   One CTA per unit (<= tu consecutive tracks of one group). thread <-> one 6x6 slot-pair block
-//   (a >= b) of the group's local (6W)^2 matrix, accumulated in registers over the unit's tracks with
-//   the E rows staged through shared memory; one flush of atomics per unit.
+//   (a >= b) of the group's local (6W)^2 matrix; fp32 products are summed over runs of kSchurRun
+//   tracks in fp32 registers and the runs are added into fp64 registers (the subtraction B - E Q E^T
+//   cancels heavily, so the long sums must not round at fp32); one flush of fp64 atomics per unit.
 // =================================================================================================
+constexpr int kSchurRun = 8;
+
 __global__ void __launch_bounds__(kSchurThreads) k_schur(PlanView pv, CallView cv, int tile_tracks) {
   constexpr int NT = kSchurThreads;
   extern __shared__ float smem[];
@@ -252,9 +270,9 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(PlanView pv, CallView c
       while ((a + 1) * (a + 2) / 2 <= x) ++a;
       b = x - a * (a + 1) / 2;
     }
-    float acc[36];
+    double acc[36];
 #pragma unroll
-    for (int k = 0; k < 36; ++k) acc[k] = 0.0f;
+    for (int k = 0; k < 36; ++k) acc[k] = 0.0;
 
     for (int tt = t0; tt < t1; tt += tile_tracks) {
       const int nt = min(tile_tracks, t1 - tt);
@@ -266,23 +284,31 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(PlanView pv, CallView c
         for (int r = tau; r < rowlen; r += NT) {
           const int pose = slot_pose[r / 6];
           if (pose_free(pose, cv)) {
-            float s = 0.0f;
-            for (int k = 0; k < nt; ++k) s += qws[k] * Es[k * rowlen + r];
+            double s = 0.0;
+            for (int k = 0; k < nt; ++k) s += (double)(qws[k] * Es[k * rowlen + r]);
             red_add(cv.y + 6 * (pose - cv.fixedp) + (r % 6), -s);
           }
         }
       }
       if (have) {
-        for (int k = 0; k < nt; ++k) {
-          const float q = qs[k];
-          const float *ea = Es + k * rowlen + 6 * a, *eb = Es + k * rowlen + 6 * b;
-          float va[6], vb[6];
+        for (int k0 = 0; k0 < nt; k0 += kSchurRun) {
+          float part[36];
 #pragma unroll
-          for (int c = 0; c < 6; ++c) { va[c] = q * ea[c]; vb[c] = eb[c]; }
+          for (int k = 0; k < 36; ++k) part[k] = 0.0f;
+          const int k1 = min(k0 + kSchurRun, nt);
+          for (int k = k0; k < k1; ++k) {
+            const float q = qs[k];
+            const float *ea = Es + k * rowlen + 6 * a, *eb = Es + k * rowlen + 6 * b;
+            float va[6], vb[6];
 #pragma unroll
-          for (int c = 0; c < 6; ++c)
+            for (int c = 0; c < 6; ++c) { va[c] = q * ea[c]; vb[c] = eb[c]; }
 #pragma unroll
-            for (int e2 = 0; e2 < 6; ++e2) acc[c * 6 + e2] += va[c] * vb[e2];
+            for (int c = 0; c < 6; ++c)
+#pragma unroll
+              for (int e2 = 0; e2 < 6; ++e2) part[c * 6 + e2] += va[c] * vb[e2];
+          }
+#pragma unroll
+          for (int k = 0; k < 36; ++k) acc[k] += (double)part[k];
         }
       }
       __syncthreads();
@@ -302,7 +328,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(PlanView pv, CallView c
 }
 
 // =================================================================================================
-// K3  reduced solve (ba.py:60-70 block_solve, :5-19 CholeskySolver, :323-325 NaN retry).
+// K3  reduced solve (ba.py:60-70 block_solve, :5-19 CholeskySolver, :323-325 NaN retry), in fp64.
 //   A = S + (ep + lm * diag S) I;  A = L L^T;  dX = A^-1 y.  One CTA; the band window
 //   [j, j+bw] x [j, j+bw] lives in shared memory as a circular buffer, columns are eliminated
 //   right-looking, the forward substitution rides along, L goes to global (band) storage and the
@@ -310,26 +336,28 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(PlanView pv, CallView c
 //   is the special case bw = 6n - 1.
 // =================================================================================================
 __global__ void __launch_bounds__(kSolveThreads) k_solve_window(CallView cv, int allow_retry) {
-  extern __shared__ float smem[];
+  extern __shared__ double dsm[];
   constexpr int NT = kSolveThreads;
   const int tau = threadIdx.x, lane = tau & 31, warp = tau >> 5;
   const int M = cv.M, bw = cv.bw, WS = bw + 1, WSP = WS | 1;
-  float *win = smem;                       // [WS][WSP]
-  float *z = win + WS * WSP;               // [M]
-  float *ls = z + M;                       // [WS]
+  double *win = dsm;                       // [WS][WSP]
+  double *z = win + WS * WSP;              // [M]
+  double *ls = z + M;                      // [WS]
   __shared__ int s_flag;
-  const float *S = cv.S;
-  float *L = cv.L;
-  auto Sg = [&](int r, int c) { return (size_t)r * cv.ld + c + cv.off; };
+  const double *S = cv.S;
+  double *L = cv.L;
+  const int ld = cv.ld, off = cv.off;
+  auto Sg = [&](int r, int c) { return (size_t)r * ld + c + off; };
+  const double ep = (double)cv.ep;
   int status = 0;
 
   for (int attempt = 0; attempt < 2; ++attempt) {
-    const float lm = attempt == 0 ? 1e-4f : 1e-3f;
+    const double lm = attempt == 0 ? 1e-4 : 1e-3;
     // ---- load rows 0..bw of the window, z = y ----
     for (int r = warp; r < min(WS, M); r += NT / 32)
       for (int c = lane; c <= r; c += 32) {
-        float v = S[Sg(r, c)];
-        if (c == r) v = v + (cv.ep + lm * v);                    // ba.py:67
+        double v = S[Sg(r, c)];
+        if (c == r) v = v + (ep + lm * v);                       // ba.py:67
         win[(r % WS) * WSP + (c % WS)] = v;
       }
     for (int r = tau; r < M; r += NT) z[r] = cv.y[r];
@@ -338,14 +366,14 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_window(CallView cv, int
     for (int j = 0; j < M; ++j) {
       __syncthreads();
       const int jm = j % WS;
-      const float piv = win[jm * WSP + jm];
-      if (!(piv > 0.0f)) { failed = true; break; }                // potrf info != 0 (incl. NaN), ba.py:11
-      const float dg = sqrtf(piv), inv = 1.0f / dg;
-      const float zj = z[j] * inv;
+      const double piv = win[jm * WSP + jm];
+      if (!(piv > 0.0)) { failed = true; break; }                 // potrf info != 0 (incl. NaN), ba.py:11
+      const double dg = sqrt(piv), inv = 1.0 / dg;
+      const double zj = z[j] * inv;
       const int nb = min(bw, M - 1 - j);
       if (tau < nb) {
         const int r = j + 1 + tau;
-        const float l = win[(r % WS) * WSP + jm] * inv;
+        const double l = win[(r % WS) * WSP + jm] * inv;
         ls[tau] = l;
         L[Sg(r, j)] = l;
       }
@@ -357,7 +385,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_window(CallView cv, int
       const int j1 = (j + 1) % WS;
       for (int rr = warp; rr < nb; rr += NT / 32) {
         int rs = j1 + rr; if (rs >= WS) rs -= WS;
-        const float lr = ls[rr];
+        const double lr = ls[rr];
         for (int cc = lane; cc <= rr; cc += 32) {
           int cs = j1 + cc; if (cs >= WS) cs -= WS;
           win[rs * WSP + cs] -= lr * ls[cc];
@@ -368,15 +396,15 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_window(CallView cv, int
       if (rn < M) {
         for (int x = tau; x <= bw; x += NT) {
           const int c = rn - bw + x;
-          float v = S[Sg(rn, c)];
-          if (c == rn) v = v + (cv.ep + lm * v);
+          double v = S[Sg(rn, c)];
+          if (c == rn) v = v + (ep + lm * v);
           win[jm * WSP + (c % WS)] = v;
         }
       }
     }
     __syncthreads();
     if (failed) {                                                   // dX = 0 (ba.py:12-13); no NaN -> no retry
-      for (int r = tau; r < M; r += NT) cv.dX[r] = 0.0f;
+      for (int r = tau; r < M; r += NT) cv.dX[r] = 0.0;
       status |= (attempt == 0) ? 1 : 4;
       break;
     }
@@ -387,13 +415,13 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_window(CallView cv, int
       for (int r = lo + warp; r <= jb; r += NT / 32)
         for (int x = lane; x <= bw; x += 32) {
           const int c = r - bw + x;
-          win[(r - lo) * WSP + x] = c >= 0 ? L[Sg(r, c)] : 0.0f;
+          win[(r - lo) * WSP + x] = c >= 0 ? L[Sg(r, c)] : 0.0;
         }
       __syncthreads();
       if (warp == 0) {
         for (int j = jb; j >= lo; --j) {
-          const float *row = win + (j - lo) * WSP;                  // row[x] = L(j, j - bw + x)
-          const float xj = z[j] / row[bw];
+          const double *row = win + (j - lo) * WSP;                 // row[x] = L(j, j - bw + x)
+          const double xj = z[j] / row[bw];
           __syncwarp();
           if (lane == 0) z[j] = xj;
           for (int x = lane; x < bw; x += 32) {
@@ -406,10 +434,82 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_window(CallView cv, int
     }
     __syncthreads();
     int nan_local = 0;
-    for (int r = tau; r < M; r += NT) { const float v = z[r]; cv.dX[r] = v; nan_local |= (v != v); }
+    for (int r = tau; r < M; r += NT) { const double v = z[r]; cv.dX[r] = v; nan_local |= (v != v); }
     if (nan_local) s_flag = 1;
     __syncthreads();
     if (s_flag && allow_retry && attempt == 0) { status |= 2; __syncthreads(); continue; }   // ba.py:324-325
+    break;
+  }
+  if (tau == 0) cv.status[0] = status;
+}
+
+// K3b  dense fallback for reduced systems whose band does not fit the shared-memory window
+//   (6n > kMaxWindow with no usable band structure: unstructured graphs, loop closures). Same
+//   algorithm on the dense lower matrix held in global memory (L2-resident), one CTA, fp64.
+//   Correct for any size; a multi-CTA blocked version is future work.
+__global__ void __launch_bounds__(kSolveThreads) k_solve_dense(CallView cv, int allow_retry) {
+  extern __shared__ double dsm[];
+  constexpr int NT = kSolveThreads;
+  const int tau = threadIdx.x;
+  const int M = cv.M;
+  double *z = dsm;            // [M]
+  double *ls = dsm + M;       // [M]
+  __shared__ int s_flag;
+  const double *S = cv.S;
+  double *L = cv.L;
+  const double ep = (double)cv.ep;
+  int status = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const double lm = attempt == 0 ? 1e-4 : 1e-3;
+    for (size_t idx = tau; idx < (size_t)M * M; idx += NT) {
+      const int r = (int)(idx / M), c = (int)(idx % M);
+      if (c > r) continue;
+      double v = S[idx];
+      if (c == r) v = v + (ep + lm * v);
+      L[idx] = v;
+    }
+    for (int r = tau; r < M; r += NT) z[r] = cv.y[r];
+    if (tau == 0) s_flag = 0;
+    bool failed = false;
+    for (int j = 0; j < M; ++j) {
+      __syncthreads();
+      const double piv = L[(size_t)j * M + j];
+      if (!(piv > 0.0)) { failed = true; break; }
+      const double dg = sqrt(piv), inv = 1.0 / dg;
+      const double zj = z[j] * inv;
+      for (int r = j + 1 + tau; r < M; r += NT) ls[r] = L[(size_t)r * M + j] * inv;
+      __syncthreads();
+      if (tau == 0) { L[(size_t)j * M + j] = dg; z[j] = zj; }
+      for (int r = j + 1 + tau; r < M; r += NT) { L[(size_t)r * M + j] = ls[r]; z[r] -= ls[r] * zj; }
+      const int nb = M - 1 - j;
+      // trailing update, lower triangle: one warp per row, lanes over columns
+      for (int rr = tau >> 5; rr < nb; rr += NT / 32) {
+        const int r = j + 1 + rr;
+        const double lr = ls[r];
+        double *row = L + (size_t)r * M;
+        for (int c = j + 1 + (tau & 31); c <= r; c += 32) row[c] -= lr * ls[c];
+      }
+    }
+    __syncthreads();
+    if (failed) {
+      for (int r = tau; r < M; r += NT) cv.dX[r] = 0.0;
+      status |= (attempt == 0) ? 1 : 4;
+      break;
+    }
+    for (int j = M - 1; j >= 0; --j) {
+      __syncthreads();
+      const double xj = z[j] / L[(size_t)j * M + j];
+      __syncthreads();
+      if (tau == 0) z[j] = xj;
+      const double *row = L + (size_t)j * M;
+      for (int c = tau; c < j; c += NT) z[c] -= row[c] * xj;
+    }
+    __syncthreads();
+    int nan_local = 0;
+    for (int r = tau; r < M; r += NT) { const double v = z[r]; cv.dX[r] = v; nan_local |= (v != v); }
+    if (nan_local) s_flag = 1;
+    __syncthreads();
+    if (s_flag && allow_retry && attempt == 0) { status |= 2; __syncthreads(); continue; }
     break;
   }
   if (tau == 0) cv.status[0] = status;
@@ -432,7 +532,7 @@ __global__ void k_backsub(PlanView pv, CallView cv, int use_dx) {
   const int lane = threadIdx.x & 31;
   if (t >= pv.m) return;
   const float2 qw = cv.Qw[t];
-  float dot = 0.0f;
+  double dot = 0.0;
   if (use_dx) {
     const int g = pv.t_grp[t];
     const int W = pv.g_W[g], rowlen = 6 * W;
@@ -441,12 +541,12 @@ __global__ void k_backsub(PlanView pv, CallView cv, int use_dx) {
     for (int r = lane; r < rowlen; r += 32) {
       const int s = r / 6;
       const int pose = slot_pose[s];
-      if (pose_free(pose, cv)) dot += row[r] * cv.dX[6 * (pose - cv.fixedp) + (r - 6 * s)];
+      if (pose_free(pose, cv)) dot += (double)row[r] * cv.dX[6 * (pose - cv.fixedp) + (r - 6 * s)];
     }
     for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
   }
   if (lane == 0) {
-    const float dz = qw.x * (qw.y - dot);
+    const float dz = (float)((double)qw.x * ((double)qw.y - dot));
     cv.dZ[t] = dz;
     const size_t k = (size_t)pv.kx[t];
     cv.patches_out[3 * k + 2] = fminf(fmaxf(cv.patches[3 * k + 2] + dz, 1e-3f), 10.0f);
@@ -461,7 +561,7 @@ __global__ void k_pose_retr(CallView cv, int N) {
   float a[6] = {0, 0, 0, 0, 0, 0};
   if (pose_free(i, cv)) {
 #pragma unroll
-    for (int c = 0; c < 6; ++c) a[c] = cv.dX[6 * (i - cv.fixedp) + c];
+    for (int c = 0; c < 6; ++c) a[c] = (float)cv.dX[6 * (i - cv.fixedp) + c];
   }
   Pose dXp = pose_exp(a);
   float tmp[7];
@@ -470,13 +570,17 @@ __global__ void k_pose_retr(CallView cv, int N) {
   pose_store(r, cv.poses_out + 7 * (size_t)i);
 }
 
-// ---- debug: expand the lower (band) storage to a dense symmetric matrix -------------------------
-__global__ void k_debug_dense(const float *S, int M, int ld, int off, int bw, float *out) {
+// ---- debug: expand the lower (band) storage to a dense symmetric matrix, cast fp64 -> fp32 --------
+__global__ void k_debug_dense(const double *S, int M, int ld, int off, int bw, float *out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * M) return;
   int r = idx / M, c = idx % M;
   if (c > r) { int t = r; r = c; c = t; }
-  out[idx] = (r - c <= bw) ? S[(size_t)r * ld + c + off] : 0.0f;
+  out[idx] = (r - c <= bw) ? (float)S[(size_t)r * ld + c + off] : 0.0f;
+}
+__global__ void k_debug_cast(const double *in, float *out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
 }
 
 static int make_call(BaPlan *pl, const BaProblem *pb, CallView *cv) {
@@ -518,7 +622,7 @@ extern "C" int ba_assemble(BaPlan *pl, const BaProblem *pb, void *stream_) {
     k_edge_pass<true><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK();
   } else {
     BA_MARK(pl, BA_STAGE_ZERO, s);
-    BA_CUDA(cudaMemsetAsync(cv.S, 0, (size_t)((cv.y - cv.S) + cv.M) * sizeof(float), s));
+    BA_CUDA(cudaMemsetAsync(cv.S, 0, (size_t)((cv.y - cv.S) + cv.M) * sizeof(double), s));
     BA_MARK(pl, BA_STAGE_EDGE, s);
     k_edge_pass<false><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK();
   }
@@ -542,7 +646,8 @@ extern "C" int ba_assemble(BaPlan *pl, const BaProblem *pb, void *stream_) {
   return BA_OK;
 }
 
-extern "C" int ba_plan_reduced_system(const BaPlan *pl, float **ptr, int64_t *n_floats) {
+extern "C" int ba_plan_reduced_system(const BaPlan *pl, double **ptr, int64_t *n_values) {
+  int64_t *n_floats = n_values;
   if (!pl || !ptr || !n_floats || pl->last_fixedp < 0) return BA_ERR_ARG;
   int n, bw, ld, off; int64_t sf;
   layout_for(pl, pl->last_fixedp, &n, &bw, &ld, &off, &sf);
@@ -561,16 +666,21 @@ extern "C" int ba_solve_update(BaPlan *pl, const BaProblem *pb, void *stream_) {
   const bool so = pb->structure_only || cv.n == 0;
   if (!so) {
     if (!(pl->ev_mask & (1u << BA_STAGE_SOLVE))) BA_MARK(pl, BA_STAGE_SOLVE, s);
-    if (cv.bw + 1 > kMaxWindow) return BA_ERR_ARG;   // dense systems beyond the window solver: not built yet
-    const int WS = cv.bw + 1, WSP = WS | 1;
-    const size_t smem = ((size_t)WS * WSP + cv.M + WS) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
       BA_CUDA(cudaFuncSetAttribute(k_solve_window, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
+      BA_CUDA(cudaFuncSetAttribute(k_solve_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
       attr_set = true;
     }
-    if (smem > 227 * 1024 - 64) return BA_ERR_ARG;
-    k_solve_window<<<1, kSolveThreads, smem, s>>>(cv, pb->monodisp ? 1 : 0); BA_LAUNCH_CHECK();
+    const int WS = cv.bw + 1, WSP = WS | 1;
+    const size_t smem = ((size_t)WS * WSP + cv.M + WS) * sizeof(double);
+    if (cv.ld != cv.M && smem <= 227 * 1024 - 64) {
+      k_solve_window<<<1, kSolveThreads, smem, s>>>(cv, pb->monodisp ? 1 : 0); BA_LAUNCH_CHECK();
+    } else {
+      const size_t smem_d = 2 * (size_t)cv.M * sizeof(double);
+      if (cv.ld != cv.M || smem_d > 227 * 1024 - 64) return BA_ERR_ARG;    // > 14k unknowns without band structure
+      k_solve_dense<<<1, kSolveThreads, smem_d, s>>>(cv, pb->monodisp ? 1 : 0); BA_LAUNCH_CHECK();
+    }
   }
   BA_MARK(pl, BA_STAGE_BACKSUB, s);
   k_patches_copy_clamp<<<(pv.NM + 255) / 256, 256, 0, s>>>(pb->patches, pb->patches_out, pv.NM); BA_LAUNCH_CHECK();
@@ -600,8 +710,8 @@ extern "C" int ba_plan_debug_dense(const BaPlan *pl, int32_t n, float *S, float 
   if (n != nn) return BA_ERR_ARG;
   const int M = 6 * nn;
   if (S && M > 0) { k_debug_dense<<<(M * M + 255) / 256, 256, 0, s>>>(pl->SY, M, ld, off, bw, S); BA_LAUNCH_CHECK(); }
-  if (y && M > 0) BA_CUDA(cudaMemcpyAsync(y, pl->SY + sf, M * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  if (dX && M > 0) BA_CUDA(cudaMemcpyAsync(dX, pl->dX, M * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (y && M > 0) { k_debug_cast<<<(M + 255) / 256, 256, 0, s>>>(pl->SY + sf, y, M); BA_LAUNCH_CHECK(); }
+  if (dX && M > 0) { k_debug_cast<<<(M + 255) / 256, 256, 0, s>>>(pl->dX, dX, M); BA_LAUNCH_CHECK(); }
   const int m = pl->v.m;
   if (Q) BA_CUDA(cudaMemcpy2DAsync(Q, sizeof(float), pl->Qw, sizeof(float2), sizeof(float), m, cudaMemcpyDeviceToDevice, s));
   if (w) BA_CUDA(cudaMemcpy2DAsync(w, sizeof(float), reinterpret_cast<float *>(pl->Qw) + 1, sizeof(float2), sizeof(float), m, cudaMemcpyDeviceToDevice, s));

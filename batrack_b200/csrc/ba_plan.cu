@@ -258,7 +258,8 @@ void layout_for(const BaPlan *p, int fixedp, int *n, int *bw, int *ld, int *off,
   int nn = std::max(p->n_total_layout - fixedp, 0);
   int M = 6 * nn;
   int b = std::min(6 * p->bwb_layout + 5, std::max(M - 1, 0));
-  if (M > 0 && b + 1 <= kMaxWindow) {     // lower band storage: S(r,c) at r*bw + c + bw
+  const size_t win_bytes = ((size_t)(b + 1) * ((b + 1) | 1) + M + b + 1) * sizeof(double);
+  if (M > 0 && b + 1 <= kMaxWindow && win_bytes <= 227 * 1024 - 64) {   // lower band storage: S(r,c) at r*bw + c + bw
     *ld = b; *off = b; *s_floats = (int64_t)M * (b + 1);
   } else {                                // dense lower storage
     b = std::max(M - 1, 0);
@@ -300,7 +301,8 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
   std::memset(&pl->info, 0, sizeof(pl->info));
   std::memset(&pl->v, 0, sizeof(pl->v));
   pl->device = dev;
-  pl->SY = pl->L = pl->Est = pl->dX = pl->dZ = nullptr;
+  pl->SY = pl->L = pl->dX = nullptr;
+  pl->Est = pl->dZ = nullptr;
   pl->Cw = pl->Qw = nullptr;
   pl->status = nullptr;
   pl->sy_floats = 0;
@@ -427,7 +429,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     PL_CUDA(own(pl, &pl->status, 4));
     PL_CUDA(cudaMemsetAsync(pl->status, 0, 4 * sizeof(int), s));
     if (alloc_workspace(pl) != BA_OK) return fail(BA_ERR_CUDA);
-    in.workspace_bytes = (int64_t)(esize + 8) * 4 + (int64_t)m * 20 + pl->sy_floats * 8;
+    in.workspace_bytes = (int64_t)(esize + 8) * 4 + (int64_t)m * 20 + pl->sy_floats * 16;
   }  // Scratch frees (stream-ordered)
   PL_CUDA(cudaStreamSynchronize(s));
 #undef PL_CUDA

@@ -51,10 +51,10 @@ class Plan:
         _capi.check(_capi.lib().ba_plan_info(self.handle, C.byref(self.info)))
 
     def reduced_system(self):
-        """Zero-copy float32 tensor view of the exchange buffer [S | y] of the last assemble."""
+        """Zero-copy float64 tensor view of the exchange buffer [S | y] of the last assemble."""
         p, n = C.c_void_p(), C.c_int64()
         _capi.check(_capi.lib().ba_plan_reduced_system(self.handle, C.byref(p), C.byref(n)), "reduced_system")
-        return _tensor_view(p.value, n.value, self.device, self)
+        return _tensor_view(p.value, n.value, self.device, self, dtype=torch.float64)
 
     def debug(self, n):
         """Dense symmetric S [6n,6n], y, dX, Q, w, dZ of the last call (tests)."""
@@ -90,7 +90,7 @@ class _RawCuda:
 
 
 def _tensor_view(ptr, n, device, owner, dtype=torch.float32):
-    typestr = "<f4" if dtype == torch.float32 else "<i4"
+    typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4"}[dtype]
     return torch.as_tensor(_RawCuda(ptr, n, typestr, owner), device=device)
 
 

@@ -111,10 +111,11 @@ int ba_step(BaPlan *plan, const BaProblem *prob, void *stream);
  * structure-only calls apart from the per-track C, w. */
 int ba_assemble(BaPlan *plan, const BaProblem *prob, void *stream);
 
-/* The exchange buffer: `n_floats` contiguous floats holding the lower (band) storage of S followed
- * by y. A sharded caller all-reduces (sum) exactly this range between ba_assemble and
- * ba_solve_update. Valid for the fixedp of the last ba_assemble. */
-int ba_plan_reduced_system(const BaPlan *plan, float **ptr, int64_t *n_floats);
+/* The exchange buffer: `n_values` contiguous DOUBLES holding the lower (band) storage of S followed
+ * by y (the reduced system is accumulated in fp64). A sharded caller all-reduces
+ * (sum) exactly this range between ba_assemble and ba_solve_update. Valid for the fixedp of the last
+ * ba_assemble. */
+int ba_plan_reduced_system(const BaPlan *plan, double **ptr, int64_t *n_values);
 
 /* Second half: damped Cholesky solve of the reduced system, depth back-substitution, retractions. */
 int ba_solve_update(BaPlan *plan, const BaProblem *prob, void *stream);
