@@ -33,6 +33,13 @@ struct PlanView {
   const int *slot_pose;    // group g's slots (ascending pose ids) at 2*g_pat[g] .. + W_g
   const int *slot_ptr;     // CSR over slots of the items feeding them, at 2*g_pat[g] + g .. + W_g + 1
   const int *slot_items;   // items (position*2 + {0: via source i, 1: via target j}) at 2*g_pat[g] ..
+  // slots fed by >= 2 items ("multi" slots) are reduced through shared memory; the others are stored
+  // directly by the one thread that produces them
+  const int *g_nm;         // [G]   number of multi slots of group g
+  const int *ms_ptr;       // ranks of the items of the k-th multi slot: [ms_ptr[k], ms_ptr[k+1]), at 2*g_pat[g] + g
+  const int *ms_slot;      // slot id of the k-th multi slot, at 2*g_pat[g]
+  const int *pat_ri, *pat_rj;  // [sum d] rank of the position's i-side / j-side item among multi items, or -1
+  int dmax;                // longest track
   const int *c_t0, *c_grp; // [n_chunks+1], [n_chunks]  edge-pass work units (track ranges)
   const int *u_t0, *u_grp; // [n_units+1],  [n_units]   Schur work units
 };
@@ -70,6 +77,7 @@ struct BaPlan {
   float2 *Cw, *Qw;
   int *status;
   int64_t sy_floats;                   // capacity of SY (elements)
+  int64_t est_floats;                  // size of Est
   int last_n, last_fixedp;             // layout of the last ba_assemble
   // staging buffers of ba_step_host
   void *host_stage;

@@ -34,180 +34,359 @@ __device__ __forceinline__ double *S_at(const CallView &c, int r, int col) {
 }
 
 // =================================================================================================
-// K1  edge pass.  One CTA per chunk (<= tc consecutive tracks of one pattern group).
+// K1  edge pass.  One CTA per chunk (<= tc consecutive tracks of one pattern group, degree d <= 256).
 //   thread <-> (track slot kappa, pattern position p); the (i,j) pair of a position is fixed, so
-//   Gij / adjoint / intrinsics are registers, and Bjj, vj are accumulated in registers over the
-//   chunk's tracks. Ji = -Ad(Gij)^T Jj (projective_ops.py:96) makes every i-side quantity a fixed
-//   linear image of the j-side one:  Bii = A Bjj A^T, Bij = -A Bjj, vi = -A vj, Eik = -A Ejk,
-//   with A = Ad(Gij)^T, applied once per position (B, v) or per edge (E).
-//   Per-edge E 6-vectors and the C, w scalars go through shared memory and are reduced per track in
-//   a fixed order into the group's dense E rows [track][slot*6+c]  (never a dense [n, m] E).
+//   Gij / adjoint / intrinsics are per-position constants (computed once per CTA, kept in registers),
+//   and Bjj, vj are accumulated in registers over the chunk's tracks. Ji = -Ad(Gij)^T Jj
+//   (projective_ops.py:96) makes every i-side quantity a fixed linear image of the j-side one:
+//       Bii = A Bjj A^T,  Bij = -A Bjj,  vi = -A vj,  Eik = -A Ejk,   A = Ad(Gij)^T,
+//   applied once per position (B, v; in fp64 at the flush) or per edge (E).
+//   E 6-vectors whose slot is fed by this edge alone are stored straight into the group's dense E rows
+//   [track][slot*6+c]; the others (e.g. the source frame's slot, fed by every edge of the track) and
+//   the C, w scalars are reduced per track through shared memory in a fixed order.
+//   No per-edge index is read: ii/jj/kk are implied by (group pattern, position, track).
 // =================================================================================================
-// staging components per edge: Eik[6] Ejk[6] c w (14); accumulators per thread: Bjj lower[21] vj[6]
-constexpr int kAccComps = 27;     // Bjj lower[21] vj[6]
+constexpr int kAccComps = 27;     // per-thread accumulators: Bjj lower[21] vj[6]
+constexpr int kPosFloats = 20;    // per-position constants: R[9] t[3] 1/fxi 1/fyi cxi cyi fxj fyj cxj cyj
+constexpr int kFlushPos = 32;     // positions flushed per round
+constexpr int kFlushOuts = 90;    // Bjj[21] Bii[21] Bij[36] vj[6] vi[6]
+constexpr int kStagePasses = 4;   // passes whose targets / weights are prefetched together (2 stages in flight)
+constexpr size_t kEdgeSmemBytes = (size_t)(kAccComps + kPosFloats + 3) * kEdgeThreads * sizeof(float) +
+                                  (size_t)2 * kStagePasses * 2 * kEdgeThreads * sizeof(float2);
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__constant__ unsigned char c_tri_a[21] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5};
+__constant__ unsigned char c_tri_b[21] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5};
 
 template <bool STRUCT_ONLY>
 __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, CallView cv) {
   constexpr int NT = kEdgeThreads;
-  __shared__ float sh[kAccComps * NT];      // staging (14*NT) during passes, accumulators (27*NT) at flush
+  extern __shared__ __align__(16) float dyn_smem[];
+  float *sh = dyn_smem;                                 // [27 NT] staging during passes; accumulators / outputs at flush
+  float *shc = sh + kAccComps * NT;                     // [20 NT] per-position constants
+  float *spatch = shc + kPosFloats * NT;                // [3 NT]  (x, y, inverse depth) of the chunk's tracks
+  float2 *sin = reinterpret_cast<float2 *>(spatch + 3 * NT);   // [2 stages][kStagePasses][2][NT] target / weight
   const int tau = threadIdx.x;
   const int chunk = blockIdx.x;
   const int g = pv.c_grp[chunk];
-  const int t0 = pv.c_t0[chunk], t1 = pv.c_t0[chunk + 1];
-  const int gt0 = pv.g_t0[g];
   const int pat0 = pv.g_pat[g];
   const int d = pv.g_pat[g + 1] - pat0;
+  if (d > NT) return;                                   // long tracks: k_edge_pass_long
+  const int t0 = pv.c_t0[chunk], t1 = pv.c_t0[chunk + 1];
+  const int gt0 = pv.g_t0[g];
   const int W = pv.g_W[g];
   const int ebase = pv.tptr[gt0];
   const int sbase = 2 * pat0;
   const int *slot_pose = pv.slot_pose + sbase;
-  const int *slot_ptr = pv.slot_ptr + sbase + g;
-  const int *slot_items = pv.slot_items + sbase;
   float *Erows = cv.Est + pv.g_eoff[g];
   const int rowlen = 6 * W;
-  const int outs_per_track = STRUCT_ONLY ? 2 : rowlen + 2;
+  const int nm = pv.g_nm[g];
+  const int *ms_ptr = pv.ms_ptr + sbase + g;
+  const int *ms_slot = pv.ms_slot + sbase;
+  const int R = ms_ptr[nm];                             // staged (multi-slot) items per track
+  const int Tp = NT / d;                                // tracks per pass
+  const bool active = tau < Tp * d;
+  const int kappa = tau / d;
+  const int p = tau - kappa * d;
+  const int estride = (Tp * R) | 1;                     // floats between staged E components
+  float *stE = sh;                                      // [6][estride]   (6*estride <= 12*NT + 6)
+  float *stC = sh + 13 * NT;                            // [2][NT]
 
-  for (int p0 = 0; p0 < d; p0 += NT) {
-    const int dc = min(d - p0, NT);
-    const int Tp = NT / dc;
-    const bool active = tau < Tp * dc;
-    const int kappa = tau / dc;
-    const int p = p0 + (tau - kappa * dc);
-
-    PairConst pc;
-    if (active) {
-      const int i = pv.pat_i[pat0 + p], j = pv.pat_j[pat0 + p];
-      pc = pair_const(cv.poses + 7 * i, cv.poses + 7 * j, cv.intr + 4 * i, cv.intr + 4 * j);
-    }
-    float acc[kAccComps];
+  // ---- the chunk's patches (gathered through kx once), and per-position constants, once per CTA ----
+  for (int x = tau; x < t1 - t0; x += NT) {
+    const float *pp = cv.patches + 3 * (size_t)__ldg(pv.kx + t0 + x);
+    spatch[x] = __ldg(pp); spatch[NT + x] = __ldg(pp + 1); spatch[2 * NT + x] = __ldg(pp + 2);
+  }
+  if (tau < d) {
+    const int i = pv.pat_i[pat0 + tau], j = pv.pat_j[pat0 + tau];
+    PairConst c = pair_const(cv.poses + 7 * i, cv.poses + 7 * j, cv.intr + 4 * i, cv.intr + 4 * j);
 #pragma unroll
-    for (int k = 0; k < kAccComps; ++k) acc[k] = 0.0f;
-
-    for (int ts = t0; ts < t1; ts += Tp) {
-      const int t = ts + kappa;
-      if (active && t < t1) {
-        const int q = ebase + (t - gt0) * d + p;
-        const int e = pv.perm_identity ? q : __ldg(pv.eperm + q);
-        float2 tg;
-        if (cv.tstride == 2) tg = __ldg(reinterpret_cast<const float2 *>(cv.targets) + e);
-        else { const float *tp = cv.targets + (size_t)e * cv.tstride; tg = make_float2(__ldg(tp), __ldg(tp + 1)); }
-        const float2 wg = __ldg(reinterpret_cast<const float2 *>(cv.weights) + e);
-        const float *pp = cv.patches + 3 * (size_t)__ldg(pv.kx + t);
-        EdgeTerms et;
-        edge_terms(pc, __ldg(pp), __ldg(pp + 1), __ldg(pp + 2), tg.x, tg.y, wg.x, wg.y, cv.bounds, cv.loss, et);
-        const float wz0 = et.w0 * et.Jz0, wz1 = et.w1 * et.Jz1;      // (w Jz)^T, ba.py:255
-        sh[12 * NT + tau] = wz0 * et.Jz0 + wz1 * et.Jz1;             // C term, ba.py:287
-        sh[13 * NT + tau] = wz0 * et.r0 + wz1 * et.r1;               // w term, ba.py:292
-        if (!STRUCT_ONLY) {
-          float Ej[6], Ei[6];
+    for (int k = 0; k < 9; ++k) shc[k * NT + tau] = c.R[k];
+    shc[9 * NT + tau] = c.t.x; shc[10 * NT + tau] = c.t.y; shc[11 * NT + tau] = c.t.z;
+    shc[12 * NT + tau] = 1.0f / c.fxi; shc[13 * NT + tau] = 1.0f / c.fyi;
+    shc[14 * NT + tau] = c.cxi; shc[15 * NT + tau] = c.cyi;
+    shc[16 * NT + tau] = c.fxj; shc[17 * NT + tau] = c.fyj; shc[18 * NT + tau] = c.cxj; shc[19 * NT + tau] = c.cyj;
+  }
+  __syncthreads();
+  PairConst pc;
+  float ifxi = 0.f, ifyi = 0.f;
+  int ri_rank = -1, rj_rank = -1, li = 0, lj = 0;
+  bool fi = false, fj = false;
+  if (active) {
 #pragma unroll
-          for (int a = 0; a < 6; ++a) {
-            const float wa0 = et.w0 * et.Jj0[a], wa1 = et.w1 * et.Jj1[a];   // (w Jj)^T, ba.py:254
-            Ej[a] = wa0 * et.Jz0 + wa1 * et.Jz1;                            // Ejk, ba.py:263
-            acc[21 + a] += wa0 * et.r0 + wa1 * et.r1;                       // vj, ba.py:266
-#pragma unroll
-            for (int b = 0; b <= a; ++b) acc[tri(a, b)] += wa0 * et.Jj0[b] + wa1 * et.Jj1[b];  // Bjj, :260
-          }
-          adjT_apply(pc.R, pc.t, Ej, Ei);                                   // Eik = -A Ejk, ba.py:262
-#pragma unroll
-          for (int a = 0; a < 6; ++a) { sh[a * NT + tau] = -Ei[a]; sh[(6 + a) * NT + tau] = Ej[a]; }
-        }
-      }
-      __syncthreads();
-      // ---- per-track reduction over pattern positions, fixed order ----
-      const int ntr = min(Tp, t1 - ts);
-      for (int o = tau; o < ntr * outs_per_track; o += NT) {
-        const int k2 = o / outs_per_track;
-        const int r = o - k2 * outs_per_track;
-        const int t = ts + k2;
-        if (!STRUCT_ONLY && r < rowlen) {
-          const int s = r / 6, comp = r - 6 * s;
-          float sum = 0.0f;
-          if (pose_free(slot_pose[s], cv)) {                                // ba.py:33-36 mask
-            for (int it = slot_ptr[s]; it < slot_ptr[s + 1]; ++it) {
-              const int item = slot_items[it];
-              const int pp2 = (item >> 1) - p0;
-              if (pp2 >= 0 && pp2 < dc) sum += sh[((item & 1) * 6 + comp) * NT + k2 * dc + pp2];
-            }
-          }
-          float *dst = Erows + (size_t)(t - gt0) * rowlen + r;
-          *dst = (p0 == 0) ? sum : *dst + sum;
-        } else {
-          const int comp = STRUCT_ONLY ? r : r - rowlen;                    // 0: C, 1: w
-          float sum = 0.0f;
-          for (int pp2 = 0; pp2 < dc; ++pp2) sum += sh[(12 + comp) * NT + k2 * dc + pp2];
-          float *dst = reinterpret_cast<float *>(cv.Cw + t) + comp;
-          *dst = (p0 == 0) ? sum : *dst + sum;
-        }
-      }
-      __syncthreads();
-    }
-
+    for (int k = 0; k < 9; ++k) pc.R[k] = shc[k * NT + p];
+    pc.t = {shc[9 * NT + p], shc[10 * NT + p], shc[11 * NT + p]};
+    ifxi = shc[12 * NT + p]; ifyi = shc[13 * NT + p];
+    pc.cxi = shc[14 * NT + p]; pc.cyi = shc[15 * NT + p];
+    pc.fxj = shc[16 * NT + p]; pc.fyj = shc[17 * NT + p]; pc.cxj = shc[18 * NT + p]; pc.cyj = shc[19 * NT + p];
     if (!STRUCT_ONLY) {
-      // ---- flush Bjj / vj of this position batch: reduce over kappa, map to the i side, scatter ----
+      ri_rank = pv.pat_ri[pat0 + p]; rj_rank = pv.pat_rj[pat0 + p];
+      li = pv.pat_li[pat0 + p]; lj = pv.pat_lj[pat0 + p];
+      fi = pose_free(slot_pose[li], cv); fj = pose_free(slot_pose[lj], cv);   // ba.py:33-39 masks
+    }
+  }
+  float acc[kAccComps];
 #pragma unroll
-      for (int k = 0; k < kAccComps; ++k) sh[k * NT + tau] = active ? acc[k] : 0.0f;
-      __syncthreads();
-      if (tau < dc) {
-        double Bl[21], vj[6];
-#pragma unroll
-        for (int k = 0; k < 21; ++k) { double s = 0.0; for (int kp = 0; kp < Tp; ++kp) s += (double)sh[k * NT + kp * dc + tau]; Bl[k] = s; }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) { double s = 0.0; for (int kp = 0; kp < Tp; ++kp) s += (double)sh[(21 + k) * NT + kp * dc + tau]; vj[k] = s; }
-        const int pi = pv.pat_i[pat0 + p0 + tau], pj = pv.pat_j[pat0 + p0 + tau];
-        const bool fi = pose_free(pi, cv), fj = pose_free(pj, cv);
-        const int ri = 6 * (pi - cv.fixedp), rj = 6 * (pj - cv.fixedp);
-        // tau < dc means kappa == 0, so this thread's pair constants `pc` are those of position p0 + tau
-        if (fj) {
-#pragma unroll
-          for (int a = 0; a < 6; ++a) {
-            red_add(cv.y + rj + a, vj[a]);                                   // ba.py:290
-#pragma unroll
-            for (int b = 0; b <= a; ++b) red_add(S_at(cv, rj + a, rj + b), Bl[tri(a, b)]);   // Bjj, ba.py:282
+  for (int k = 0; k < kAccComps; ++k) acc[k] = 0.0f;
+  const int outs_per_track = STRUCT_ONLY ? 2 : 6 * nm + 2;
+
+  // ---- targets / weights: each thread prefetches its own edges, kStagePasses passes per cp.async group,
+  //      two groups in flight; the loads of a whole stage overlap instead of one round trip per pass ----
+  const int npass = (t1 - t0 + Tp - 1) / Tp;
+  const int nstage = (npass + kStagePasses - 1) / kStagePasses;
+  auto issue_stage = [&](int st) {
+    if (active) {
+      float2 *buf = sin + (size_t)(st & 1) * kStagePasses * 2 * NT;
+      for (int k = 0; k < kStagePasses; ++k) {
+        const int t = t0 + (st * kStagePasses + k) * Tp + kappa;
+        if (t < t1) {
+          const int q = ebase + (t - gt0) * d + p;
+          const int e = pv.perm_identity ? q : __ldg(pv.eperm + q);
+          if (cv.tstride == 2) cp_async8(buf + (2 * k) * NT + tau, cv.targets + 2 * (size_t)e);
+          else {
+            const float *tp = cv.targets + (size_t)e * cv.tstride;
+            float *dstf = reinterpret_cast<float *>(buf + (2 * k) * NT + tau);
+            cp_async4(dstf, tp); cp_async4(dstf + 1, tp + 1);
           }
+          cp_async8(buf + (2 * k + 1) * NT + tau, cv.weights + 2 * (size_t)e);
         }
-        if (fi) {
-          double AB[6][6];                     // A * Bjj   (column c of Bjj is its row c)
+      }
+    }
+    cp_async_commit();
+  };
+  issue_stage(0);
+
+  for (int ps = 0; ps < npass; ++ps) {
+    const int ts = t0 + ps * Tp;
+    const int st = ps / kStagePasses, kk = ps - st * kStagePasses;
+    if (kk == 0) {
+      if (st + 1 < nstage) { issue_stage(st + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    }
+    const int t = ts + kappa;
+    if (active && t < t1) {
+      const float2 *buf = sin + (size_t)(st & 1) * kStagePasses * 2 * NT;
+      const float2 tg = buf[(2 * kk) * NT + tau], wg = buf[(2 * kk + 1) * NT + tau];
+      const int tl = t - t0;
+      const float ppx = spatch[tl], ppy = spatch[NT + tl], ppd = spatch[2 * NT + tl];
+      EdgeTerms et;
+      edge_terms(pc, ifxi, ifyi, ppx, ppy, ppd, tg.x, tg.y, wg.x, wg.y, cv.bounds, cv.loss, et);
+      const float wz0 = et.w0 * et.Jz0, wz1 = et.w1 * et.Jz1;      // (w Jz)^T, ba.py:255
+      stC[tau] = wz0 * et.Jz0 + wz1 * et.Jz1;                      // C term, ba.py:287
+      stC[NT + tau] = wz0 * et.r0 + wz1 * et.r1;                   // w term, ba.py:292
+      if (!STRUCT_ONLY) {
+        float Ej[6], Ei[6];
 #pragma unroll
-          for (int c = 0; c < 6; ++c) {
-            double col[6], out[6];
+        for (int a = 0; a < 6; ++a) {
+          const float wa0 = et.w0 * et.Jj0[a], wa1 = et.w1 * et.Jj1[a];   // (w Jj)^T, ba.py:254
+          Ej[a] = wa0 * et.Jz0 + wa1 * et.Jz1;                            // Ejk, ba.py:263
+          acc[21 + a] += wa0 * et.r0 + wa1 * et.r1;                       // vj, ba.py:266
 #pragma unroll
-            for (int a = 0; a < 6; ++a) col[a] = a >= c ? Bl[tri(a, c)] : Bl[tri(c, a)];
-            adjT_apply_d(pc.R, pc.t, col, out);
+          for (int b = 0; b <= a; ++b) acc[tri(a, b)] += wa0 * et.Jj0[b] + wa1 * et.Jj1[b];  // Bjj, :260
+        }
+        adjT_apply(pc.R, pc.t, Ej, Ei);                                   // Eik = -A Ejk, ba.py:262
+        float *row = Erows + (size_t)(t - gt0) * rowlen;
+        if (rj_rank >= 0) {
 #pragma unroll
-            for (int a = 0; a < 6; ++a) AB[a][c] = out[a];
-          }
-          double vi[6];
-          adjT_apply_d(pc.R, pc.t, vj, vi);
+          for (int a = 0; a < 6; ++a) stE[a * estride + kappa * R + rj_rank] = Ej[a];
+        } else {
+          float2 *dst = reinterpret_cast<float2 *>(row + 6 * lj);         // 24-byte aligned rows: float2 is safe
+          dst[0] = fj ? make_float2(Ej[0], Ej[1]) : make_float2(0.f, 0.f);
+          dst[1] = fj ? make_float2(Ej[2], Ej[3]) : make_float2(0.f, 0.f);
+          dst[2] = fj ? make_float2(Ej[4], Ej[5]) : make_float2(0.f, 0.f);
+        }
+        if (ri_rank >= 0) {
 #pragma unroll
-          for (int a = 0; a < 6; ++a) {
-            red_add(cv.y + ri + a, -vi[a]);                                  // vi = -A vj, ba.py:289
-            double row[6];
-            adjT_apply_d(pc.R, pc.t, AB[a], row);                            // Bii = (A Bjj) A^T, ba.py:279
+          for (int a = 0; a < 6; ++a) stE[a * estride + kappa * R + ri_rank] = -Ei[a];
+        } else {
+          float2 *dst = reinterpret_cast<float2 *>(row + 6 * li);
+          dst[0] = fi ? make_float2(-Ei[0], -Ei[1]) : make_float2(0.f, 0.f);
+          dst[1] = fi ? make_float2(-Ei[2], -Ei[3]) : make_float2(0.f, 0.f);
+          dst[2] = fi ? make_float2(-Ei[4], -Ei[5]) : make_float2(0.f, 0.f);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- per-track reduction of the staged terms, fixed order ----
+    const int ntr = min(Tp, t1 - ts);
+    for (int o = tau; o < ntr * outs_per_track; o += NT) {
+      const int k2 = o / outs_per_track;
+      const int r = o - k2 * outs_per_track;
+      const int t = ts + k2;
+      if (!STRUCT_ONLY && r < 6 * nm) {
+        const int ms = r / 6, comp = r - 6 * ms;
+        const int s = ms_slot[ms];
+        float sum = 0.0f;
+        if (pose_free(slot_pose[s], cv)) {
+          const float *src = stE + comp * estride + k2 * R;
+          for (int x = ms_ptr[ms]; x < ms_ptr[ms + 1]; ++x) sum += src[x];
+        }
+        Erows[(size_t)(t - gt0) * rowlen + 6 * s + comp] = sum;
+      } else {
+        const int comp = STRUCT_ONLY ? r : r - 6 * nm;                    // 0: C, 1: w
+        const float *src = stC + comp * NT + k2 * d;
+        float sum = 0.0f;
+        for (int x = 0; x < d; ++x) sum += src[x];
+        reinterpret_cast<float *>(cv.Cw + t)[comp] = sum;
+      }
+    }
+    __syncthreads();
+  }
+
+  if (!STRUCT_ONLY) {
+    // ---- flush: reduce Bjj / vj over kappa (fp64), map to the i side, scatter with fp64 atomics ----
 #pragma unroll
-            for (int b = 0; b <= a; ++b) red_add(S_at(cv, ri + a, ri + b), row[b]);
-          }
-          if (fj) {                            // Bij = -A Bjj (rows i, cols j); Bji = Bij^T, ba.py:280-281
-            if (pi > pj) {
+    for (int k = 0; k < kAccComps; ++k) sh[k * NT + tau] = active ? acc[k] : 0.0f;
+    __syncthreads();
+    double Bl[21], vj[6];
+    if (tau < d) {
 #pragma unroll
-              for (int a = 0; a < 6; ++a)
+      for (int k = 0; k < 21; ++k) { double s = 0.0; for (int kp = 0; kp < Tp; ++kp) s += (double)sh[k * NT + kp * d + tau]; Bl[k] = s; }
 #pragma unroll
-                for (int b = 0; b < 6; ++b) red_add(S_at(cv, ri + a, rj + b), -AB[a][b]);
-            } else if (pi < pj) {
+      for (int k = 0; k < 6; ++k) { double s = 0.0; for (int kp = 0; kp < Tp; ++kp) s += (double)sh[(21 + k) * NT + kp * d + tau]; vj[k] = s; }
+    }
+    __syncthreads();
+    double *outD = reinterpret_cast<double *>(sh);          // [kFlushPos][kFlushOuts] doubles = 23 KB <= 27 KB
+    for (int pb = 0; pb < d; pb += kFlushPos) {
+      if (tau >= pb && tau < min(pb + kFlushPos, d)) {       // tau < d: kappa == 0, so `pc` belongs to position tau
+        double *o = outD + (tau - pb) * kFlushOuts;
+        double AB[6][6];                                     // A * Bjj   (column c of Bjj is its row c)
 #pragma unroll
-              for (int a = 0; a < 6; ++a)
+        for (int c = 0; c < 6; ++c) {
+          double col[6], out[6];
 #pragma unroll
-                for (int b = 0; b < 6; ++b) red_add(S_at(cv, rj + b, ri + a), -AB[a][b]);
-            } else {
+          for (int a = 0; a < 6; ++a) col[a] = a >= c ? Bl[tri(a, c)] : Bl[tri(c, a)];
+          adjT_apply_d(pc.R, pc.t, col, out);
 #pragma unroll
-              for (int a = 0; a < 6; ++a)
+          for (int a = 0; a < 6; ++a) AB[a][c] = out[a];
+        }
+        double vi[6];
+        adjT_apply_d(pc.R, pc.t, vj, vi);
 #pragma unroll
-                for (int b = 0; b <= a; ++b) red_add(S_at(cv, ri + a, ri + b), -(AB[a][b] + AB[b][a]));
-            }
-          }
+        for (int k = 0; k < 21; ++k) o[k] = Bl[k];                                    // Bjj, ba.py:282
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          double row[6];
+          adjT_apply_d(pc.R, pc.t, AB[a], row);                                       // Bii = (A Bjj) A^T, ba.py:279
+#pragma unroll
+          for (int b = 0; b <= a; ++b) o[21 + tri(a, b)] = row[b];
+#pragma unroll
+          for (int b = 0; b < 6; ++b) o[42 + 6 * a + b] = -AB[a][b];                  // Bij = -A Bjj, ba.py:280
+          o[78 + a] = vj[a];                                                          // ba.py:290
+          o[84 + a] = -vi[a];                                                         // vi = -A vj, ba.py:289
         }
       }
       __syncthreads();
+      const int np = min(kFlushPos, d - pb);
+      for (int x = tau; x < np * kFlushOuts; x += NT) {
+        const int pl = x / kFlushOuts, o = x - pl * kFlushOuts;
+        const int pi = pv.pat_i[pat0 + pb + pl], pj = pv.pat_j[pat0 + pb + pl];
+        const bool f_i = pose_free(pi, cv), f_j = pose_free(pj, cv);
+        const int ri = 6 * (pi - cv.fixedp), rj = 6 * (pj - cv.fixedp);
+        const double val = outD[x];
+        if (o < 21) {
+          if (f_j) red_add(S_at(cv, rj + c_tri_a[o], rj + c_tri_b[o]), val);
+        } else if (o < 42) {
+          if (f_i) red_add(S_at(cv, ri + c_tri_a[o - 21], ri + c_tri_b[o - 21]), val);
+        } else if (o < 78) {
+          if (f_i && f_j) {                                  // Bij (rows i, cols j) and Bji = Bij^T, ba.py:280-281
+            const int a = (o - 42) / 6, b = (o - 42) - 6 * a;
+            if (pi > pj) red_add(S_at(cv, ri + a, rj + b), val);
+            else if (pi < pj) red_add(S_at(cv, rj + b, ri + a), val);
+            else if (a >= b) red_add(S_at(cv, ri + a, ri + b), val + outD[pl * kFlushOuts + 42 + 6 * b + a]);
+          }
+        } else if (o < 84) {
+          if (f_j) red_add(cv.y + rj + (o - 78), val);
+        } else {
+          if (f_i) red_add(cv.y + ri + (o - 84), val);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// K1-long: tracks with more than 256 edges (do not occur in BA-Track's graphs, S_slam * steps <= 72;
+// kept so that the operator is total). One thread per edge, float atomics into pre-zeroed E rows / Cw,
+// fp64 atomics into S / y. Slow path.
+template <bool STRUCT_ONLY>
+__global__ void k_edge_pass_long(PlanView pv, CallView cv) {
+  const int chunk = blockIdx.x;
+  const int g = pv.c_grp[chunk];
+  const int pat0 = pv.g_pat[g];
+  const int d = pv.g_pat[g + 1] - pat0;
+  if (d <= kEdgeThreads) return;
+  const int t0 = pv.c_t0[chunk], t1 = pv.c_t0[chunk + 1];
+  const int gt0 = pv.g_t0[g];
+  const int W = pv.g_W[g], rowlen = 6 * W;
+  const int ebase = pv.tptr[gt0];
+  const int *slot_pose = pv.slot_pose + 2 * pat0;
+  float *Erows = cv.Est + pv.g_eoff[g];
+  const long long total = (long long)(t1 - t0) * d;
+  for (long long x = threadIdx.x; x < total; x += blockDim.x) {
+    const int t = t0 + (int)(x / d), p = (int)(x % d);
+    const int i = pv.pat_i[pat0 + p], j = pv.pat_j[pat0 + p];
+    const PairConst pc = pair_const(cv.poses + 7 * i, cv.poses + 7 * j, cv.intr + 4 * i, cv.intr + 4 * j);
+    const int q = ebase + (t - gt0) * d + p;
+    const int e = pv.perm_identity ? q : pv.eperm[q];
+    const float *tp = cv.targets + (size_t)e * cv.tstride, *wp = cv.weights + 2 * (size_t)e;
+    const float *pp = cv.patches + 3 * (size_t)pv.kx[t];
+    EdgeTerms et;
+    edge_terms(pc, 1.0f / pc.fxi, 1.0f / pc.fyi, pp[0], pp[1], pp[2], tp[0], tp[1], wp[0], wp[1], cv.bounds, cv.loss, et);
+    const float wz0 = et.w0 * et.Jz0, wz1 = et.w1 * et.Jz1;
+    atomicAdd(reinterpret_cast<float *>(cv.Cw + t), wz0 * et.Jz0 + wz1 * et.Jz1);
+    atomicAdd(reinterpret_cast<float *>(cv.Cw + t) + 1, wz0 * et.r0 + wz1 * et.r1);
+    if (STRUCT_ONLY) continue;
+    const bool fi = pose_free(i, cv), fj = pose_free(j, cv);
+    const int li = pv.pat_li[pat0 + p], lj = pv.pat_lj[pat0 + p];
+    (void)slot_pose;
+    float Ej[6], Ei[6], vjf[6];
+    double Bl[21], vj[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const float wa0 = et.w0 * et.Jj0[a], wa1 = et.w1 * et.Jj1[a];
+      Ej[a] = wa0 * et.Jz0 + wa1 * et.Jz1;
+      vjf[a] = wa0 * et.r0 + wa1 * et.r1;
+      vj[a] = (double)vjf[a];
+#pragma unroll
+      for (int b = 0; b <= a; ++b) Bl[tri(a, b)] = (double)(wa0 * et.Jj0[b] + wa1 * et.Jj1[b]);
+    }
+    adjT_apply(pc.R, pc.t, Ej, Ei);
+    float *row = Erows + (size_t)(t - gt0) * rowlen;
+    if (fj) for (int a = 0; a < 6; ++a) atomicAdd(row + 6 * lj + a, Ej[a]);
+    if (fi) for (int a = 0; a < 6; ++a) atomicAdd(row + 6 * li + a, -Ei[a]);
+    const int ri = 6 * (i - cv.fixedp), rj = 6 * (j - cv.fixedp);
+    if (fj) for (int a = 0; a < 6; ++a) {
+      red_add(cv.y + rj + a, vj[a]);
+      for (int b = 0; b <= a; ++b) red_add(S_at(cv, rj + a, rj + b), Bl[tri(a, b)]);
+    }
+    if (fi) {
+      double AB[6][6], vi[6];
+      for (int c = 0; c < 6; ++c) {
+        double col[6], out[6];
+        for (int a = 0; a < 6; ++a) col[a] = a >= c ? Bl[tri(a, c)] : Bl[tri(c, a)];
+        adjT_apply_d(pc.R, pc.t, col, out);
+        for (int a = 0; a < 6; ++a) AB[a][c] = out[a];
+      }
+      adjT_apply_d(pc.R, pc.t, vj, vi);
+      for (int a = 0; a < 6; ++a) {
+        red_add(cv.y + ri + a, -vi[a]);
+        double rowd[6];
+        adjT_apply_d(pc.R, pc.t, AB[a], rowd);
+        for (int b = 0; b <= a; ++b) red_add(S_at(cv, ri + a, ri + b), rowd[b]);
+        if (fj) for (int b = 0; b < 6; ++b) {
+          if (i > j) red_add(S_at(cv, ri + a, rj + b), -AB[a][b]);
+          else if (i < j) red_add(S_at(cv, rj + b, ri + a), -AB[a][b]);
+          else if (a >= b) red_add(S_at(cv, ri + a, ri + b), -(AB[a][b] + AB[b][a]));
+        }
+      }
     }
   }
 }
@@ -335,17 +514,27 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(PlanView pv, CallView c
 //   backward substitution streams it back in blocks of rows. A dense system with 6n <= kMaxWindow
 //   is the special case bw = 6n - 1.
 // =================================================================================================
+// 1/sqrt(x) in fp64 from the fp32 SFU seed + two Newton steps (rel. error ~1e-15); avoids the slow
+// DSQRT + DDIV sequences on the critical path of every pivot
+__device__ __forceinline__ double rsqrt_fast(double x) {
+  double y = (double)rsqrtf((float)x);
+  y = y * (1.5 - 0.5 * x * y * y);
+  y = y * (1.5 - 0.5 * x * y * y);
+  y = y * (1.5 - 0.5 * x * y * y);
+  return y;
+}
+
 __global__ void __launch_bounds__(kSolveThreads) k_solve_window(CallView cv, int allow_retry) {
   extern __shared__ double dsm[];
-  constexpr int NT = kSolveThreads;
+  constexpr int NT = kSolveThreads, NW = NT / 32;
   const int tau = threadIdx.x, lane = tau & 31, warp = tau >> 5;
   const int M = cv.M, bw = cv.bw, WS = bw + 1, WSP = WS | 1;
   double *win = dsm;                       // [WS][WSP]
   double *z = win + WS * WSP;              // [M]
   double *ls = z + M;                      // [WS]
   __shared__ int s_flag;
-  const double *S = cv.S;
-  double *L = cv.L;
+  const double *__restrict__ S = cv.S;
+  double *__restrict__ L = cv.L;
   const int ld = cv.ld, off = cv.off;
   auto Sg = [&](int r, int c) { return (size_t)r * ld + c + off; };
   const double ep = (double)cv.ep;
@@ -354,7 +543,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_window(CallView cv, int
   for (int attempt = 0; attempt < 2; ++attempt) {
     const double lm = attempt == 0 ? 1e-4 : 1e-3;
     // ---- load rows 0..bw of the window, z = y ----
-    for (int r = warp; r < min(WS, M); r += NT / 32)
+    for (int r = warp; r < min(WS, M); r += NW)
       for (int c = lane; c <= r; c += 32) {
         double v = S[Sg(r, c)];
         if (c == r) v = v + (ep + lm * v);                       // ba.py:67
@@ -363,12 +552,31 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_window(CallView cv, int
     for (int r = tau; r < M; r += NT) z[r] = cv.y[r];
     if (tau == 0) s_flag = 0;
     bool failed = false;
+    // the row that enters the window after column j is prefetched one column ahead into registers
+    constexpr int PF = (kMaxWindow + NT - 1) / NT;
+    double pf[PF];
+    auto prefetch_row = [&](int rn) {
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int x = tau + u * NT;
+        pf[u] = 0.0;
+        if (rn < M && x <= bw) {
+          const int c = rn - bw + x;
+          double v = S[Sg(rn, c)];
+          if (c == rn) v = v + (ep + lm * v);
+          pf[u] = v;
+        }
+      }
+    };
+    prefetch_row(WS);
     for (int j = 0; j < M; ++j) {
       __syncthreads();
       const int jm = j % WS;
       const double piv = win[jm * WSP + jm];
       if (!(piv > 0.0)) { failed = true; break; }                 // potrf info != 0 (incl. NaN), ba.py:11
-      const double dg = sqrt(piv), inv = 1.0 / dg;
+      double inv, dg;
+      if (piv > 1e-30 && piv < 1e30) { inv = rsqrt_fast(piv); dg = piv * inv; }
+      else { dg = sqrt(piv); inv = 1.0 / dg; }
       const double zj = z[j] * inv;
       const int nb = min(bw, M - 1 - j);
       if (tau < nb) {
@@ -381,24 +589,42 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_window(CallView cv, int
       __syncthreads();
       if (tau == 0) z[j] = zj;
       if (tau < nb) z[j + 1 + tau] -= ls[tau] * zj;
-      // rank-1 update of the trailing window, lower triangle
-      const int j1 = (j + 1) % WS;
-      for (int rr = warp; rr < nb; rr += NT / 32) {
-        int rs = j1 + rr; if (rs >= WS) rs -= WS;
-        const double lr = ls[rr];
-        for (int cc = lane; cc <= rr; cc += 32) {
-          int cs = j1 + cc; if (cs >= WS) cs -= WS;
-          win[rs * WSP + cs] -= lr * ls[cc];
-        }
-      }
-      // bring in row j + WS (reuses the shared-memory row of the retired row j)
+      // store the prefetched row j + WS (reuses the shared-memory row of the retired row j) and
+      // start fetching the next one
       const int rn = j + WS;
       if (rn < M) {
-        for (int x = tau; x <= bw; x += NT) {
-          const int c = rn - bw + x;
-          double v = S[Sg(rn, c)];
-          if (c == rn) v = v + (ep + lm * v);
-          win[jm * WSP + (c % WS)] = v;
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+          const int x = tau + u * NT;
+          if (x <= bw) win[jm * WSP + ((rn - bw + x) % WS)] = pf[u];
+        }
+      }
+      prefetch_row(rn + 1);
+      // rank-1 update of the trailing window, lower triangle: warp <-> rows, lanes <-> columns. Fixed
+      // trip counts + full unrolling so that every load of a thread is in flight before the first FMA.
+      const int j1 = (j + 1) % WS;
+      constexpr int RU = (kMaxWindow + NW - 1) / NW, CU = (kMaxWindow + 31) / 32;
+#pragma unroll
+      for (int k = 0; k < RU; ++k) {
+        const int rr = warp + k * NW;
+        if (rr < nb) {
+          int rs = j1 + rr; if (rs >= WS) rs -= WS;
+          const double lr = ls[rr];
+          double *wrow = win + rs * WSP;
+          double lc[CU], wv[CU];
+          int cs[CU];
+#pragma unroll
+          for (int u = 0; u < CU; ++u) {
+            const int cc = lane + 32 * u;
+            int c2 = j1 + cc; if (c2 >= WS) c2 -= WS;
+            cs[u] = c2;
+            const bool on = cc <= rr;
+            lc[u] = on ? ls[cc] : 0.0;
+            wv[u] = on ? wrow[c2] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < CU; ++u)
+            if (lane + 32 * u <= rr) wrow[cs[u]] = wv[u] - lr * lc[u];
         }
       }
     }
@@ -412,7 +638,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_window(CallView cv, int
     for (int jb = M - 1; jb >= 0; jb -= WS) {
       const int lo = max(jb - WS + 1, 0);
       __syncthreads();
-      for (int r = lo + warp; r <= jb; r += NT / 32)
+      for (int r = lo + warp; r <= jb; r += NW)
         for (int x = lane; x <= bw; x += 32) {
           const int c = r - bw + x;
           win[(r - lo) * WSP + x] = c >= 0 ? L[Sg(r, c)] : 0.0;
@@ -617,14 +843,27 @@ extern "C" int ba_assemble(BaPlan *pl, const BaProblem *pb, void *stream_) {
   const bool so = pb->structure_only || cv.n == 0;                 // ba.py:316
   pl->last_n = cv.n; pl->last_fixedp = pb->fixedp;
   pl->ev_mask = 0;
+  static bool edge_attr_set = false;
+  if (!edge_attr_set) {
+    BA_CUDA(cudaFuncSetAttribute(k_edge_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
+    BA_CUDA(cudaFuncSetAttribute(k_edge_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
+    edge_attr_set = true;
+  }
+  const bool has_long = pv.dmax > kEdgeThreads;
+  if (has_long) {   // the slow path accumulates with atomics: its targets start from zero
+    BA_CUDA(cudaMemsetAsync(cv.Cw, 0, (size_t)pv.m * sizeof(float2), s));
+    if (!so) BA_CUDA(cudaMemsetAsync(cv.Est, 0, (size_t)pl->est_floats * sizeof(float), s));
+  }
   if (so) {
     BA_MARK(pl, BA_STAGE_EDGE, s);
-    k_edge_pass<true><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK();
+    k_edge_pass<true><<<pv.n_chunks, kEdgeThreads, kEdgeSmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK();
+    if (has_long) { k_edge_pass_long<true><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
   } else {
     BA_MARK(pl, BA_STAGE_ZERO, s);
     BA_CUDA(cudaMemsetAsync(cv.S, 0, (size_t)((cv.y - cv.S) + cv.M) * sizeof(double), s));
     BA_MARK(pl, BA_STAGE_EDGE, s);
-    k_edge_pass<false><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK();
+    k_edge_pass<false><<<pv.n_chunks, kEdgeThreads, kEdgeSmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK();
+    if (has_long) { k_edge_pass_long<false><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
   }
   BA_MARK(pl, BA_STAGE_TRACKQ, s);
   k_track_q<<<(pv.m + 255) / 256, 256, 0, s>>>(pv, cv); BA_LAUNCH_CHECK();

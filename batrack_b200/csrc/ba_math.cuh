@@ -165,10 +165,12 @@ BA_HD float robust_weight(float r, int loss) {        // ba.py:81-100
   return 1.0f;
 }
 
-BA_HD void edge_terms(const PairConst &c, float px, float py, float pd, float tx, float ty, float wx, float wy,
-                      const float *bounds, int loss, EdgeTerms &o) {
+// ifxi / ifyi = 1/fx_i, 1/fy_i (per-position constants; (x - cx) * (1/fx) differs from the reference's
+// (x - cx) / fx by at most one fp32 ulp)
+BA_HD void edge_terms(const PairConst &c, float ifxi, float ifyi, float px, float py, float pd, float tx, float ty,
+                      float wx, float wy, const float *bounds, int loss, EdgeTerms &o) {
   // iproj (projective_ops.py:19-29)
-  float x0 = (px - c.cxi) / c.fxi, y0 = (py - c.cyi) / c.fyi;
+  float x0 = (px - c.cxi) * ifxi, y0 = (py - c.cyi) * ifyi;
   // act4 (se3.h:53-56): R * X0[:3] + t * X0[3]
   float X = c.R[0] * x0 + c.R[1] * y0 + c.R[2] + c.t.x * pd;
   float Y = c.R[3] * x0 + c.R[4] * y0 + c.R[5] + c.t.y * pd;

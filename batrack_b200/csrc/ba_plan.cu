@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -107,12 +108,16 @@ __global__ void k_fill_groups(const int *__restrict__ gflag, const int *__restri
   if (t == m - 1) g_t0[g + 1] = m;
 }
 
-// Work units = pieces of at most `tc` consecutive tracks of one group.
+// Work units = a group's tracks split into the fewest equal pieces of at most `tc` consecutive tracks.
 __global__ void k_chunk_flags(const int *__restrict__ t_grp, const int *__restrict__ g_t0, int m, int tc,
                               int *__restrict__ cflag) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m) return;
-  cflag[t] = ((t - g_t0[t_grp[t]]) % tc == 0) ? 1 : 0;
+  const int g = t_grp[t];
+  const int T = g_t0[g + 1] - g_t0[g];
+  const int pieces = (T + tc - 1) / tc;
+  const int len = (T + pieces - 1) / pieces;
+  cflag[t] = ((t - g_t0[g]) % len == 0) ? 1 : 0;
 }
 __global__ void k_fill_chunks(const int *__restrict__ cflag, const int *__restrict__ cinc,
                               const int *__restrict__ t_grp, int m, int *__restrict__ c_t0,
@@ -137,6 +142,8 @@ __global__ void k_group_slots(const int *__restrict__ g_t0, const int *__restric
                               int *__restrict__ pat_i, int *__restrict__ pat_j, int *__restrict__ pat_li,
                               int *__restrict__ pat_lj, int *__restrict__ slot_pose,
                               int *__restrict__ slot_ptr, int *__restrict__ slot_items,
+                              int *__restrict__ g_nm, int *__restrict__ ms_ptr, int *__restrict__ ms_slot,
+                              int *__restrict__ pat_ri, int *__restrict__ pat_rj,
                               int *__restrict__ g_W, long long *__restrict__ g_esz, int *__restrict__ meta) {
   extern __shared__ unsigned sm[];
   const int g = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -202,6 +209,21 @@ __global__ void k_group_slots(const int *__restrict__ g_t0, const int *__restric
         }
       }
     }
+    // multi slots (>= 2 items) and the rank of their items in slot order
+    int *mp = ms_ptr + sbase + g, *msl = ms_slot + sbase;
+    int nm = 0, R = 0;
+    for (int p = 0; p < d; ++p) { pat_ri[pat0 + p] = -1; pat_rj[pat0 + p] = -1; }
+    for (int s = 0; s < W; ++s) {
+      if (sp[s + 1] - sp[s] < 2) continue;
+      mp[nm] = R;
+      msl[nm++] = s;
+      for (int x = sp[s]; x < sp[s + 1]; ++x) {
+        const int item = it[x];
+        if (item & 1) pat_rj[pat0 + (item >> 1)] = R++; else pat_ri[pat0 + (item >> 1)] = R++;
+      }
+    }
+    mp[nm] = R;
+    g_nm[g] = nm;
     g_W[g] = W;
     g_esz[g] = (long long)T * 6 * W;
     atomicMax(&meta[META_WMAX], W);
@@ -372,8 +394,12 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
 
     // work units: edge-pass chunks and Schur units (fewer, larger: their flush is (6W)^2 atomics)
     const int sms = 148;
-    int tc = std::min(64, std::max(8, cdiv(m, 2 * sms)));
+    // edge pass: about one wave of CTAs (2 resident per SM) — per-CTA set-up and flush are amortised over
+    // more tracks; Schur: units of <= 128 tracks. BA_EDGE_TC / BA_SCHUR_TU override for experiments.
+    int tc = std::min(256, std::max(8, cdiv(m, sms)));
     int tu = std::min(128, std::max(16, 16 * cdiv(cdiv(m, 2 * sms), 16)));
+    if (const char *e = getenv("BA_EDGE_TC")) tc = std::max(1, atoi(e));
+    if (const char *e = getenv("BA_SCHUR_TU")) tu = std::max(1, atoi(e));
     int *cflag, *cinc;
     PL_CUDA(sc.get(&cflag, m)); PL_CUDA(sc.get(&cinc, m));
     int counts[2] = {0, 0};
@@ -391,7 +417,9 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     int pat_total = 0;
     PL_CUDA(cudaMemcpyAsync(&pat_total, g_pat + G, sizeof(int), cudaMemcpyDeviceToHost, s));
     PL_CUDA(cudaStreamSynchronize(s));
-    int *pat_i, *pat_j, *pat_li, *pat_lj, *slot_pose, *slot_ptr, *slot_items;
+    int *pat_i, *pat_j, *pat_li, *pat_lj, *slot_pose, *slot_ptr, *slot_items, *g_nm, *ms_ptr, *ms_slot, *pat_ri, *pat_rj;
+    PL_CUDA(own(pl, &g_nm, G)); PL_CUDA(own(pl, &pat_ri, pat_total)); PL_CUDA(own(pl, &pat_rj, pat_total));
+    PL_CUDA(own(pl, &ms_slot, 2 * (size_t)pat_total)); PL_CUDA(own(pl, &ms_ptr, 2 * (size_t)pat_total + G + 1));
     PL_CUDA(own(pl, &pat_i, pat_total)); PL_CUDA(own(pl, &pat_j, pat_total));
     PL_CUDA(own(pl, &pat_li, pat_total)); PL_CUDA(own(pl, &pat_lj, pat_total));
     PL_CUDA(own(pl, &slot_pose, 2 * (size_t)pat_total)); PL_CUDA(own(pl, &slot_items, 2 * (size_t)pat_total));
@@ -400,7 +428,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
       int nwords = (N + 31) / 32;
       size_t smem = (size_t)(2 * nwords + 1) * sizeof(int);
       k_group_slots<<<G, 128, smem, s>>>(g_t0, g_pat, tptr, sij, N, pat_i, pat_j, pat_li, pat_lj, slot_pose,
-                                         slot_ptr, slot_items, g_W, g_esz, meta); PL_LAUNCH();
+                                         slot_ptr, slot_items, g_nm, ms_ptr, ms_slot, pat_ri, pat_rj, g_W, g_esz, meta); PL_LAUNCH();
     }
     k_zero_last<<<1, 1, 0, s>>>(g_esz, G); PL_LAUNCH();
     PL_CUDA(exclusive_sum(sc, g_esz, g_eoff, G + 1, s));
@@ -415,6 +443,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     v.eperm = eperm; v.kx = kx; v.tptr = tptr; v.t_grp = t_grp; v.g_t0 = g_t0; v.g_pat = g_pat; v.g_W = g_W;
     v.g_eoff = g_eoff; v.pat_i = pat_i; v.pat_j = pat_j; v.pat_li = pat_li; v.pat_lj = pat_lj;
     v.slot_pose = slot_pose; v.slot_ptr = slot_ptr; v.slot_items = slot_items;
+    v.g_nm = g_nm; v.ms_ptr = ms_ptr; v.ms_slot = ms_slot; v.pat_ri = pat_ri; v.pat_rj = pat_rj; v.dmax = hmeta[META_DMAX];
     v.c_t0 = unit_t0[0]; v.c_grp = unit_grp[0]; v.u_t0 = unit_t0[1]; v.u_grp = unit_grp[1];
 
     BaPlanInfo &in = pl->info;
@@ -425,6 +454,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     pl->bwb_layout = in.block_bandwidth;
 
     PL_CUDA(own(pl, &pl->Est, (size_t)esize + 8));
+    pl->est_floats = esize;
     PL_CUDA(own(pl, &pl->Cw, m)); PL_CUDA(own(pl, &pl->Qw, m)); PL_CUDA(own(pl, &pl->dZ, m));
     PL_CUDA(own(pl, &pl->status, 4));
     PL_CUDA(cudaMemsetAsync(pl->status, 0, 4 * sizeof(int), s));

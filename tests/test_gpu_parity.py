@@ -53,7 +53,7 @@ def test_stagewise_against_oracle(name):
     dbg = {k: v.cpu().numpy() for k, v in plan.debug(n).items()}
     errs = {k: rel_err(dbg[k], parts[k].numpy()) for k in ("S", "y", "Q", "w", "dX", "dZ")}
     print(f"\n{name}: " + "  ".join(f"{k} {v:.1e}" for k, v in errs.items()))
-    assert errs["S"] < 2e-5 and errs["y"] < 2e-5 and errs["Q"] < 1e-5 and errs["w"] < 2e-5
+    assert errs["S"] < 2e-5 and errs["y"] < 2e-5 and errs["Q"] < 1e-5 and errs["w"] < 1e-4   # w sums residuals: ~eps*|pixel|/|r|
     assert errs["dX"] < TOL and errs["dZ"] < 5 * TOL
     assert plan.status() == 0
 
