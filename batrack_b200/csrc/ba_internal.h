@@ -72,7 +72,7 @@ struct BaPlan {
   int n_total_layout, bwb_layout;      // what the reduced-system layout uses (>= the local values)
   int device;
   // workspace
-  double *SY, *L, *dX;
+  double *SY, *L, *dX, *Wg;            // Wg: inverted diagonal tiles of the tensor-core solver
   float *Est, *dZ;
   float2 *Cw, *Qw;
   int *status;
@@ -93,6 +93,9 @@ namespace ba {
 extern std::atomic<long long> g_launches;
 int set_cuda_error(cudaError_t e, const char *what);
 void layout_for(const BaPlan *p, int fixedp, int *n, int *bw, int *ld, int *off, int64_t *s_floats);
+constexpr int kMmaMaxBw = 120;        // widest band the 16x16-tile register window of the DMMA solver covers
+size_t solve_mma_smem_bytes(int M);
+int launch_solve_band_mma(const CallView &cv, int allow_retry, double *Wg, cudaStream_t s);
 }  // namespace ba
 
 #define BA_CUDA(call)                                                         \

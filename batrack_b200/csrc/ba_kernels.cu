@@ -1,6 +1,7 @@
 // ba_kernels.cu — the BA iteration: edge pass, per-track Schur complement, reduced solve,
 // back-substitution and retractions (reference: main/backend/ba.py:217-339 and the projective_ops /
 // lietorch code it calls). See DESIGN.md for the data layout and the roofline of each kernel.
+#include <cstdlib>
 #include <cstring>
 
 #include "ba_internal.h"
@@ -913,7 +914,12 @@ extern "C" int ba_solve_update(BaPlan *pl, const BaProblem *pb, void *stream_) {
     }
     const int WS = cv.bw + 1, WSP = WS | 1;
     const size_t smem = ((size_t)WS * WSP + cv.M + WS) * sizeof(double);
-    if (cv.ld != cv.M && smem <= 227 * 1024 - 64) {
+    static const char *force = getenv("BA_SOLVER");        // "window" / "dense": force a fallback (tests, A/B timing)
+    const bool want_mma = !force || !force[0] || force[0] == 'm';
+    if (want_mma && cv.ld != cv.M && cv.bw <= kMmaMaxBw && solve_mma_smem_bytes(cv.M) <= 227 * 1024 - 64) {
+      rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, s);
+      if (rc) return rc;
+    } else if (cv.ld != cv.M && smem <= 227 * 1024 - 64 && !(force && force[0] == 'd')) {
       k_solve_window<<<1, kSolveThreads, smem, s>>>(cv, pb->monodisp ? 1 : 0); BA_LAUNCH_CHECK();
     } else {
       const size_t smem_d = 2 * (size_t)cv.M * sizeof(double);

@@ -299,6 +299,7 @@ static int alloc_workspace(BaPlan *pl) {
     BA_CUDA(own(pl, &pl->SY, need));
     BA_CUDA(own(pl, &pl->L, sf + 8));
     BA_CUDA(own(pl, &pl->dX, 6 * (size_t)n + 8));
+    BA_CUDA(own(pl, &pl->Wg, 8 * (6 * (size_t)n + 8)));
     pl->sy_floats = need;
   }
   pl->info.banded = (ld != 6 * n) ? 1 : 0;
@@ -323,7 +324,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
   std::memset(&pl->info, 0, sizeof(pl->info));
   std::memset(&pl->v, 0, sizeof(pl->v));
   pl->device = dev;
-  pl->SY = pl->L = pl->dX = nullptr;
+  pl->SY = pl->L = pl->dX = pl->Wg = nullptr;
   pl->Est = pl->dZ = nullptr;
   pl->Cw = pl->Qw = nullptr;
   pl->status = nullptr;
