@@ -24,7 +24,9 @@ namespace ba {
 
 constexpr int kMmaThreads = 256, kMmaWarps = 8;
 constexpr int kTilesPerWarp = 17;
+constexpr int kBackStages = 4;     // tile rows of L in flight during the back substitution
 constexpr int kPs = 12;            // row stride (doubles) of the shared 8x8 tiles: conflict-free fragment loads
+constexpr int kTs = 8 * kPs;       // doubles per shared tile
 
 // the 136 unordered pairs {x <= y} of the 16 circular tile positions, diagonal-major; pair idx belongs
 // to warp idx % 8 as its (idx / 8)-th tile. Every position appears in exactly 2 tiles of every warp.
@@ -47,10 +49,11 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 
 __device__ __forceinline__ double rsqrt64(double x) {
   double y = (double)rsqrtf((float)x);
-  y = y * (1.5 - 0.5 * x * y * y);
-  y = y * (1.5 - 0.5 * x * y * y);
-  y = y * (1.5 - 0.5 * x * y * y);
-  return y;
+  // fp32 seed (rel. error ~2e-7) + one Newton step -> ~6e-14. The factor is then exact for a matrix that
+  // differs from A by 1e-13 relative, five orders below what the fp32 edge terms carry.
+  const double hy = 0.5 * y;
+  return fma(fma(-x * y, hy, 0.5), y, y);  // y + y * (0.5 - 0.5 x y^2)
+
 }
 
 __device__ __forceinline__ void cp_async8_d(void *smem_dst, const void *gsrc) {
@@ -66,11 +69,17 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
   const int M = cv.M, bw = cv.bw, ld = cv.ld, off = cv.off;
   const int NT8 = (M + 7) >> 3, Mp = NT8 * 8;
   double *z = dsm;                         // [Mp]   right-hand side -> forward solution -> solution
-  double *Psm = z + Mp;                    // [16][8][kPs]  panel tiles L_aJ by circular position
-  double *Dsm = Psm + 16 * 8 * kPs;        // [8][kPs]      raw diagonal tile
+  double *Psm = z + Mp;                    // [17][8][kPs]  panel tiles L_aJ by circular position; tile 16 = zeros
+  double *Nsm = Psm + 17 * kTs;            // [17][8][kPs]  the same, negated (A operand of C -= L L^T)
+  double *Dsm = Nsm + 17 * kTs;            // [8][kPs]      raw diagonal tile
   double *Wsm = Dsm + 8 * kPs;             // [8][kPs]      W = L_JJ^-1
   double *zJ = Wsm + 8 * kPs;              // [8]
-  double *Lst = zJ + 8;                    // [2][8][128 + 64] back-substitution stages: 8 rows of L + W_J
+  double *dd = zJ + 8;                     // [Mp]  damping ep + lm * S_rr, added when a diagonal tile is factored
+  double *Lst = dd + Mp;                   // [kBackStages][8][128 + 64] back-substitution stages: 8 rows of L + W_J
+  unsigned *tabU = reinterpret_cast<unsigned *>(Lst + kBackStages * (8 * 128 + 64));   // [16][136] operand offsets of [U]
+  unsigned *tabP = tabU + 16 * 136;        // [16][8] which (two) of a warp's 17 tiles touch position e
+  unsigned *tabX = tabP + 16 * 8;          // [16][8] the other position of those two tiles, 8 bits each
+  double *xs = reinterpret_cast<double *>(tabX + 16 * 8);          // [8] x_J of the back substitution
   __shared__ int s_fail, s_nan;
   const double *__restrict__ S = cv.S;
   double *__restrict__ L = cv.L;
@@ -78,15 +87,40 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
   auto Sg = [&](int r, int c) { return (size_t)r * ld + c + off; };
   int status = 0;
 
+  // ---- step tables: which operand tiles every register tile needs when position e leaves the window ----
+  for (int o = tau; o < 16 * 136; o += kMmaThreads) {
+    const int e = o / 136, idx = o - e * 136;
+    const int x = c_px[idx], y = c_py[idx];
+    unsigned offA = 16 * kTs, offB = 16 * kTs;                      // inactive tile: both operands = the zero tile
+    if (x != e && y != e) {
+      const int ax = (x - e) & 15, ay = (y - e) & 15;
+      offA = (ax > ay ? x : y) * kTs;                               // row tile = larger global index
+      offB = (ax > ay ? y : x) * kTs;
+    }
+    tabU[o] = offA | (offB << 16);
+  }
+  for (int o = tau; o < 16 * 8; o += kMmaThreads) {
+    const int e = o >> 3, w = o & 7;
+    unsigned m = 0, xo = 0;
+    int k = 0;
+    for (int t = 0; t < kTilesPerWarp; ++t) {
+      const int x = c_px[t * 8 + w], y = c_py[t * 8 + w];
+      if (x == e || y == e) { m |= 1u << t; xo |= (unsigned)(x == e ? y : x) << (8 * k++); }
+    }
+    tabP[o] = m;
+    tabX[o] = xo;
+  }
+  for (int o = tau; o < kTs; o += kMmaThreads) { Psm[16 * kTs + o] = 0.0; Nsm[16 * kTs + o] = 0.0; }
+
   for (int attempt = 0; attempt < 2; ++attempt) {
     const double lm = attempt == 0 ? 1e-4 : 1e-3;
-    // value of the damped matrix at (r, c), r >= c, with identity padding beyond M
+    // value of S at (r, c), r >= c, with identity padding beyond M. The damping of the diagonal
+    // (ba.py:67) is added from `dd` when the diagonal tile is factored, so that nothing here consumes the
+    // loaded value and the global latency of a refill hides behind the rest of the step.
     auto Aval = [&](int r, int c) -> double {
       if (r >= M) return r == c ? 1.0 : 0.0;
       if (c > r || r - c > bw) return 0.0;
-      double v = S[Sg(r, c)];
-      if (r == c) v = v + (ep + lm * v);                        // ba.py:67
-      return v;
+      return S[Sg(r, c)];
     };
     auto load_tile = [&](int a, int b, double &c0, double &c1) {   // tile (a, b), a >= b, C-fragment layout
       const int r = 8 * a + g, c = 8 * b + 2 * q;
@@ -94,7 +128,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
       c1 = Aval(r, c + 1);
     };
 
-    for (int r = tau; r < Mp; r += kMmaThreads) z[r] = r < M ? cv.y[r] : 0.0;
+    for (int r = tau; r < Mp; r += kMmaThreads) {
+      z[r] = r < M ? cv.y[r] : 0.0;
+      dd[r] = r < M ? ep + lm * S[Sg(r, r)] : 0.0;                 // A = S + (ep + lm * S) .* I, ba.py:67
+    }
     if (tau == 0) { s_fail = 0; s_nan = 0; }
     double ct[kTilesPerWarp][2];
 #pragma unroll
@@ -105,14 +142,35 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
     }
     bool failed = false;
 
+    // The two tiles of this warp that touch the retiring position e are worked on in fixed registers
+    // (et) so that the unrolled code can interleave them; their refills (rf) are loaded during [P] and
+    // merged back into the tile registers one step later, when the loads have long landed.
+    double rf[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    unsigned pm_prev = 0;
+
     for (int J = 0; J < NT8; ++J) {
       const int e = J & 15;
-      __syncthreads();                                             // previous [U] done with Psm
-      // ---- [D] diagonal tile -> shared ----
+      const unsigned pm = tabP[e * 8 + warp], xo2 = tabX[e * 8 + warp];
+      double et[2][2];
+      {
+        int kp = 0, kc = 0;
 #pragma unroll
-      for (int t = 0; t < kTilesPerWarp; ++t) {
-        const int x = c_px[t * 8 + warp], y = c_py[t * 8 + warp];
-        if (x == e && y == e) { Dsm[g * kPs + 2 * q] = ct[t][0]; Dsm[g * kPs + 2 * q + 1] = ct[t][1]; }
+        for (int t = 0; t < kTilesPerWarp; ++t) {
+          if ((pm_prev >> t) & 1u) { ct[t][0] = kp ? rf[1][0] : rf[0][0]; ct[t][1] = kp ? rf[1][1] : rf[0][1]; ++kp; }
+          if ((pm >> t) & 1u) {
+            if (kc == 0) { et[0][0] = ct[t][0]; et[0][1] = ct[t][1]; } else { et[1][0] = ct[t][0]; et[1][1] = ct[t][1]; }
+            ++kc;
+          }
+        }
+      }
+      pm_prev = pm;
+      const int xo0 = xo2 & 0xff, xo1 = (xo2 >> 8) & 0xff;
+      __syncthreads();                                             // previous [U] done with Psm / Nsm
+      // ---- [D] diagonal tile (+ damping) -> shared. Pair {e,e} is the first e-tile of warp e%8. ----
+      if (xo0 == e) {
+        const double dmp = dd[8 * J + g];
+        Dsm[g * kPs + 2 * q] = et[0][0] + (2 * q == g ? dmp : 0.0);
+        Dsm[g * kPs + 2 * q + 1] = et[0][1] + (2 * q + 1 == g ? dmp : 0.0);
       }
       __syncthreads();
       if (warp == 0) {
@@ -131,7 +189,6 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
           const bool fast = piv > 1e-30 && piv < 1e30;
           const double inv = fast ? rsqrt64(piv) : 1.0 / sqrt(piv);
           invd[k] = inv;
-          a[tri8(k, k)] = piv * inv;
 #pragma unroll
           for (int i = k + 1; i < 8; ++i) a[tri8(i, k)] *= inv;
 #pragma unroll
@@ -141,101 +198,89 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
         }
         if (!ok) { if (lane == 0) s_fail = 1; }
         else {
-          // L_JJ to global (band storage), rows < M only
-          if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-              for (int j = 0; j <= i; ++j)
-                if (8 * J + i < M) L[Sg(8 * J + i, 8 * J + j)] = a[tri8(i, j)];
-          }
-          // forward substitution of the block with L_JJ: zJ = L_JJ^-1 z_J
-          double zo[8];
+          // (L_JJ itself is never needed again: the back substitution uses W_J.)
+          // One forward substitution per lane, same instruction stream, different right-hand side:
+          // lanes 0..7 solve L_JJ w = e_lane (column `lane` of W = L_JJ^-1), lane 8 solves L_JJ zJ = z_J.
+          double wv[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            double s = z[8 * J + i];
+            double s = lane == 8 ? z[8 * J + i] : (lane == i ? 1.0 : 0.0);
 #pragma unroll
-            for (int j = 0; j < i; ++j) s -= a[tri8(i, j)] * zo[j];
-            zo[i] = s * invd[i];
+            for (int j = 0; j < i; ++j) s -= a[tri8(i, j)] * wv[j];
+            wv[i] = s * invd[i];
           }
-          if (lane == 0) {
+          if (lane < 8) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { z[8 * J + i] = zo[i]; zJ[i] = zo[i]; }
-          }
-          // W = L_JJ^-1 (lower triangular), one column at a time straight to shared / global memory
+            for (int i = 0; i < 8; ++i) Wsm[i * kPs + lane] = wv[i];
+          } else if (lane == 8) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            double wc[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) wc[i] = 0.0;
-            wc[j] = invd[j];
-#pragma unroll
-            for (int i = j + 1; i < 8; ++i) {
-              double s = 0.0;
-#pragma unroll
-              for (int m2 = j; m2 < i; ++m2) s += a[tri8(i, m2)] * wc[m2];
-              wc[i] = -s * invd[i];
-            }
-            if (lane == 0) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { Wsm[i * kPs + j] = wc[i]; Wg[(size_t)J * 64 + i * 8 + j] = wc[i]; }
-            }
+            for (int i = 0; i < 8; ++i) { z[8 * J + i] = wv[i]; zJ[i] = wv[i]; }
           }
         }
       }
       __syncthreads();
       if (s_fail) { failed = true; break; }
-      // ---- [P] panel tiles: L_aJ = A_aJ W^T; refill the registers with the entering tile row ----
+      // ---- [P] panel tiles: L_aJ = A_aJ W^T; both e-tiles in one straight-line block. A tile below the
+      //      matrix is all zeros and yields zeros; the diagonal tile only skips its stores. ----
+      if (warp == kMmaWarps - 1) {                                  // W_J -> global for the back substitution
+        Wg[(size_t)J * 64 + lane] = Wsm[(lane >> 3) * kPs + (lane & 7)];
+        Wg[(size_t)J * 64 + 32 + lane] = Wsm[(4 + (lane >> 3)) * kPs + (lane & 7)];
+      }
       {
         const double wb0 = Wsm[g * kPs + q], wb1 = Wsm[g * kPs + 4 + q];   // B[k][n] = W[n][k], n = g, k = 4s + q
+        const double zq0 = zJ[2 * q], zq1 = zJ[2 * q + 1];
+        const int lo = g * kPs + 2 * q;
+        const int src0 = (lane & ~3) | (q >> 1), src1 = src0 + 2;
+        const int cJ = 8 * J + 2 * q;
+        const int an = J + 16;
+        double p[2][2], part[2];
+        int xo[2] = {xo0, xo1}, ag[2];
 #pragma unroll
-        for (int t = 0; t < kTilesPerWarp; ++t) {
-          const int x = c_px[t * 8 + warp], y = c_py[t * 8 + warp];
-          if (x != e && y != e) continue;
-          const int xo = (x == e) ? y : x;                         // the other position (== e for the diagonal tile)
-          const int a = J + ((xo - e) & 15);                       // global tile row held at position xo
-          if (xo != e && a < NT8) {
-            // C fragment (cols 2q, 2q+1 of row g) -> A fragments (col 4s + q of row g)
-            const int src0 = (lane & ~3) | (q >> 1), src1 = (lane & ~3) | (2 + (q >> 1));
-            const double v00 = __shfl_sync(0xffffffffu, ct[t][0], src0), v01 = __shfl_sync(0xffffffffu, ct[t][1], src0);
-            const double v10 = __shfl_sync(0xffffffffu, ct[t][0], src1), v11 = __shfl_sync(0xffffffffu, ct[t][1], src1);
-            const double a0 = (q & 1) ? v01 : v00, a1 = (q & 1) ? v11 : v10;
-            double p0, p1;
-            dmma884(p0, p1, a0, wb0, 0.0, 0.0);
-            dmma884(p0, p1, a1, wb1, p0, p1);
-            double *pt = Psm + (xo * 8 + g) * kPs + 2 * q;
-            pt[0] = p0; pt[1] = p1;
-            const int r = 8 * a + g, c = 8 * J + 2 * q;
+        for (int k = 0; k < 2; ++k) {
+          ag[k] = J + ((xo[k] - e) & 15);                          // global tile row held at position xo
+          // C fragment (cols 2q, 2q+1 of row g) -> A fragments (col 4s + q of row g)
+          const double v00 = __shfl_sync(0xffffffffu, et[k][0], src0), v01 = __shfl_sync(0xffffffffu, et[k][1], src0);
+          const double v10 = __shfl_sync(0xffffffffu, et[k][0], src1), v11 = __shfl_sync(0xffffffffu, et[k][1], src1);
+          const double a0 = (q & 1) ? v01 : v00, a1 = (q & 1) ? v11 : v10;
+          dmma884(p[k][0], p[k][1], a0, wb0, 0.0, 0.0);
+          dmma884(p[k][0], p[k][1], a1, wb1, p[k][0], p[k][1]);
+          part[k] = p[k][0] * zq0 + p[k][1] * zq1;                 // right-hand side: z_a -= L_aJ zJ
+          part[k] += __shfl_xor_sync(0xffffffffu, part[k], 1);
+          part[k] += __shfl_xor_sync(0xffffffffu, part[k], 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const bool panel = xo[k] != e;
+          const int r = 8 * ag[k] + g;
+          if (panel) {
+            Psm[xo[k] * kTs + lo] = p[k][0]; Psm[xo[k] * kTs + lo + 1] = p[k][1];
+            Nsm[xo[k] * kTs + lo] = -p[k][0]; Nsm[xo[k] * kTs + lo + 1] = -p[k][1];
+            if (q == 0 && r < Mp) z[r] -= part[k];
             if (r < M) {                                           // columns of tile J are < M whenever a row below is
-              if (r - c <= bw) L[Sg(r, c)] = p0;
-              if (r - c - 1 <= bw) L[Sg(r, c + 1)] = p1;
+              double *lp = L + Sg(r, cJ);
+              if (r - cJ <= bw) lp[0] = p[k][0];
+              if (r - cJ - 1 <= bw) lp[1] = p[k][1];
             }
-            // right-hand side: z_a -= L_aJ zJ
-            double part = p0 * zJ[2 * q] + p1 * zJ[2 * q + 1];
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            if (q == 0) z[r] -= part;
-          } else if (xo != e) {
-            // warp-uniform branch: nothing to do for tiles below the matrix
           }
           // refill: position e now stands for tile index J + 16
-          const int an = J + 16, bn = (xo == e) ? J + 16 : a;
-          ct[t][0] = ct[t][1] = 0.0;
-          if (an < NT8) load_tile(an, bn, ct[t][0], ct[t][1]);
+          rf[k][0] = rf[k][1] = 0.0;
+          if (an < NT8) load_tile(an, panel ? ag[k] : an, rf[k][0], rf[k][1]);
         }
       }
       __syncthreads();
-      // ---- [U] trailing update: C_ab -= L_aJ L_bJ^T ----
+      // ---- [U] trailing update: C_ab -= L_aJ L_bJ^T, branch-free. Operand offsets come from the step
+      //      table; the e-tiles (whose registers are stale until the refill is merged) and tiles below the
+      //      matrix read zeros. ----
+      {
+        const unsigned *tu = tabU + e * 136 + warp;
+        const double *An = Nsm + g * kPs + q, *Bp = Psm + g * kPs + q;
 #pragma unroll
-      for (int t = 0; t < kTilesPerWarp; ++t) {
-        const int x = c_px[t * 8 + warp], y = c_py[t * 8 + warp];
-        if (x == e || y == e) continue;
-        const int ax = J + ((x - e) & 15), ay = J + ((y - e) & 15);
-        const int pa = ax > ay ? x : y, pb = ax > ay ? y : x;       // row tile = larger global index
-        if (max(ax, ay) >= NT8) continue;
-        const double *A = Psm + (pa * 8 + g) * kPs + q, *B = Psm + (pb * 8 + g) * kPs + q;
-        dmma884(ct[t][0], ct[t][1], -A[0], B[0], ct[t][0], ct[t][1]);
-        dmma884(ct[t][0], ct[t][1], -A[4], B[4], ct[t][0], ct[t][1]);
+        for (int t = 0; t < kTilesPerWarp; ++t) {
+          const unsigned o = tu[t * 8];
+          const double *A = An + (o & 0xffffu), *B = Bp + (o >> 16);
+          dmma884(ct[t][0], ct[t][1], A[0], B[0], ct[t][0], ct[t][1]);
+          dmma884(ct[t][0], ct[t][1], A[4], B[4], ct[t][0], ct[t][1]);
+        }
       }
     }
     __syncthreads();
@@ -262,34 +307,38 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     __threadfence_block();
-    stage_load(NT8 - 1, (NT8 - 1) & 1);
+    // kBackStages - 1 stages in flight: one (possibly empty) cp.async group per tile row
+    for (int k = 0; k < kBackStages - 1; ++k) {
+      if (NT8 - 1 - k >= 0) stage_load(NT8 - 1 - k, (NT8 - 1 - k) % kBackStages);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int J = NT8 - 1; J >= 0; --J) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(kBackStages - 2) : "memory");
       __syncthreads();                                             // stage J landed; iteration J+1 fully retired
-      if (J > 0) stage_load(J - 1, (J - 1) & 1);                   // overlaps this iteration
-      const double *st = Lst + (size_t)(J & 1) * (8 * 128 + 64);
+      if (J - (kBackStages - 1) >= 0) stage_load(J - (kBackStages - 1), (J - (kBackStages - 1)) % kBackStages);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      const double *st = Lst + (size_t)(J % kBackStages) * (8 * 128 + 64);
       const double *Wj = st + 8 * 128;                             // W_J row-major 8x8
-      // x_J = W_J^T z_J. The 120 column threads need all 8 values (registers, static indices); the 8
-      // writer threads compute their own component.
-      double xJ[8];
+      // x_J = W_J^T z_J : 8 threads, one component each (two partial sums to halve the FMA chain)
+      if (tau < 8) {
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = i; k < 8; ++k) s += Wj[k * 8 + i] * z[8 * J + k];
-        xJ[i] = s;
+        for (int k = 0; k < 8; k += 2) {
+          s0 += (k >= tau ? Wj[k * 8 + tau] : 0.0) * z[8 * J + k];
+          s1 += (k + 1 >= tau ? Wj[(k + 1) * 8 + tau] : 0.0) * z[8 * J + k + 1];
+        }
+        __syncwarp(0xffu);                                         // all 8 lanes have read z_J
+        xs[tau] = s0 + s1;
+        z[8 * J + tau] = s0 + s1;
       }
-      double xmine = 0.0;
-      if (tau < 8) for (int k = tau; k < 8; ++k) xmine += Wj[k * 8 + tau] * z[8 * J + k];
-      __syncthreads();                                             // everyone has read z_J
-      if (tau < 8) z[8 * J + tau] = xmine;
+      __syncthreads();
       if (tau >= 32 && tau < 32 + 120) {
         const int xcol = tau - 32, c = 8 * (J - 15) + xcol;
         if (c >= 0) {
-          double s = 0.0;
+          double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-          for (int gg = 0; gg < 8; ++gg) s += st[gg * 128 + xcol] * xJ[gg];
-          z[c] -= s;
+          for (int gg = 0; gg < 8; gg += 2) { s0 += st[gg * 128 + xcol] * xs[gg]; s1 += st[(gg + 1) * 128 + xcol] * xs[gg + 1]; }
+          z[c] -= s0 + s1;
         }
       }
     }
@@ -306,7 +355,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
 
 size_t solve_mma_smem_bytes(int M) {
   const int Mp = ((M + 7) / 8) * 8;
-  return ((size_t)Mp + 16 * 8 * kPs + 2 * 8 * kPs + 8 + 2 * (8 * 128 + 64)) * sizeof(double);
+  return ((size_t)2 * Mp + 2 * 17 * kTs + 2 * kTs + 8 + kBackStages * (8 * 128 + 64)) * sizeof(double) +
+         (16 * 136 + 2 * 16 * 8) * sizeof(unsigned) + 8 * sizeof(double);
 }
 
 int launch_solve_band_mma(const CallView &cv, int allow_retry, double *Wg, cudaStream_t s) {
