@@ -319,6 +319,12 @@ def main():
     except Exception:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_rank / (edge_ms * 1e-3) / 1e9 if edge_ms > 0 else None
+    traffic = None
+    try:        # DRAM bytes of the same kernel from the committed ncu --set full capture (N = 1 only)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_edge_pass"]
+        traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if world == 1 else None
+    except Exception:
+        pass
     tot = sum(stages.values()) or 1.0
     out = {
         "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -337,7 +343,7 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "k_edge_pass (residual + Jacobian + per-track reduction)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": None, "algorithmic_bytes": alg_rank, "kernel_ms": edge_ms, "peak_source": peak_src},
+                     "traffic": traffic, "algorithmic_bytes": alg_rank, "kernel_ms": edge_ms, "peak_source": peak_src},
         "kernels": {k: {"ms": v, "share": v / tot} for k, v in stages.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
