@@ -22,7 +22,8 @@
 
 namespace ba {
 
-constexpr int kMmaThreads = 256, kMmaWarps = 8;
+constexpr int kMmaWarps = 8;                 // tile warps; warp 8 is the factor warp
+constexpr int kMmaThreads = 32 * (kMmaWarps + 1);
 constexpr int kTilesPerWarp = 17;
 constexpr int kBackStages = 4;     // tile rows of L in flight during the back substitution
 constexpr int kPs = 12;            // row stride (doubles) of the shared 8x8 tiles: conflict-free fragment loads
@@ -55,6 +56,11 @@ __device__ __forceinline__ double rsqrt64(double x) {
   return fma(fma(-x * y, hy, 0.5), y, y);  // y + y * (0.5 - 0.5 x y^2)
 
 }
+
+// named barriers (id 0 is __syncthreads): 1 = panel tiles complete (tile warps), 2 = diagonal tile published
+// (owner warp -> factor warp), 3 = W_J / zJ ready (factor warp -> tile warps; also closes the previous [U])
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ void cp_async8_d(void *smem_dst, const void *gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
@@ -133,47 +139,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
       dd[r] = r < M ? ep + lm * S[Sg(r, r)] : 0.0;                 // A = S + (ep + lm * S) .* I, ba.py:67
     }
     if (tau == 0) { s_fail = 0; s_nan = 0; }
-    double ct[kTilesPerWarp][2];
-#pragma unroll
-    for (int t = 0; t < kTilesPerWarp; ++t) {
-      const int x = c_px[t * 8 + warp], y = c_py[t * 8 + warp];   // x <= y: initial window holds tile (y, x)
-      ct[t][0] = ct[t][1] = 0.0;
-      if (y < NT8) load_tile(y, x, ct[t][0], ct[t][1]);
-    }
+    __syncthreads();                                               // z, dd, tables, zero tiles visible
     bool failed = false;
-
-    // The two tiles of this warp that touch the retiring position e are worked on in fixed registers
-    // (et) so that the unrolled code can interleave them; their refills (rf) are loaded during [P] and
-    // merged back into the tile registers one step later, when the loads have long landed.
-    double rf[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-    unsigned pm_prev = 0;
-
-    for (int J = 0; J < NT8; ++J) {
-      const int e = J & 15;
-      const unsigned pm = tabP[e * 8 + warp], xo2 = tabX[e * 8 + warp];
-      double et[2][2];
-      {
-        int kp = 0, kc = 0;
-#pragma unroll
-        for (int t = 0; t < kTilesPerWarp; ++t) {
-          if ((pm_prev >> t) & 1u) { ct[t][0] = kp ? rf[1][0] : rf[0][0]; ct[t][1] = kp ? rf[1][1] : rf[0][1]; ++kp; }
-          if ((pm >> t) & 1u) {
-            if (kc == 0) { et[0][0] = ct[t][0]; et[0][1] = ct[t][1]; } else { et[1][0] = ct[t][0]; et[1][1] = ct[t][1]; }
-            ++kc;
-          }
-        }
-      }
-      pm_prev = pm;
-      const int xo0 = xo2 & 0xff, xo1 = (xo2 >> 8) & 0xff;
-      __syncthreads();                                             // previous [U] done with Psm / Nsm
-      // ---- [D] diagonal tile (+ damping) -> shared. Pair {e,e} is the first e-tile of warp e%8. ----
-      if (xo0 == e) {
-        const double dmp = dd[8 * J + g];
-        Dsm[g * kPs + 2 * q] = et[0][0] + (2 * q == g ? dmp : 0.0);
-        Dsm[g * kPs + 2 * q + 1] = et[0][1] + (2 * q + 1 == g ? dmp : 0.0);
-      }
-      __syncthreads();
-      if (warp == 0) {
+    if (warp == kMmaWarps) {
+      // =================== factor warp: [A] for column J while the tile warps still update column J-1 ==========
+      for (int J = 0; J < NT8; ++J) {
+        bar_sync(2, 64);                                           // tile (J,J) (+ damping) is in Dsm, z_J is final
         // every lane factors the 8x8 block redundantly in registers (no divergence, no extra exchange)
         double a[36];
 #pragma unroll
@@ -196,18 +167,17 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
 #pragma unroll
             for (int i = j; i < 8; ++i) a[tri8(i, j)] -= a[tri8(i, k)] * a[tri8(j, k)];
         }
-        if (!ok) { if (lane == 0) s_fail = 1; }
-        else {
+        if (ok) {
           // (L_JJ itself is never needed again: the back substitution uses W_J.)
           // One forward substitution per lane, same instruction stream, different right-hand side:
           // lanes 0..7 solve L_JJ w = e_lane (column `lane` of W = L_JJ^-1), lane 8 solves L_JJ zJ = z_J.
           double wv[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            double s = lane == 8 ? z[8 * J + i] : (lane == i ? 1.0 : 0.0);
+            double sv = lane == 8 ? z[8 * J + i] : (lane == i ? 1.0 : 0.0);
 #pragma unroll
-            for (int j = 0; j < i; ++j) s -= a[tri8(i, j)] * wv[j];
-            wv[i] = s * invd[i];
+            for (int j = 0; j < i; ++j) sv -= a[tri8(i, j)] * wv[j];
+            wv[i] = sv * invd[i];
           }
           if (lane < 8) {
 #pragma unroll
@@ -216,70 +186,130 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
 #pragma unroll
             for (int i = 0; i < 8; ++i) { z[8 * J + i] = wv[i]; zJ[i] = wv[i]; }
           }
+        } else if (lane == 0) {
+          s_fail = 1;
         }
+        bar_arrive(3, kMmaThreads);                                // W_J, zJ (or the failure flag) published
+        if (!ok) { failed = true; break; }
       }
-      __syncthreads();
-      if (s_fail) { failed = true; break; }
-      // ---- [P] panel tiles: L_aJ = A_aJ W^T; both e-tiles in one straight-line block. A tile below the
-      //      matrix is all zeros and yields zeros; the diagonal tile only skips its stores. ----
-      if (warp == kMmaWarps - 1) {                                  // W_J -> global for the back substitution
-        Wg[(size_t)J * 64 + lane] = Wsm[(lane >> 3) * kPs + (lane & 7)];
-        Wg[(size_t)J * 64 + 32 + lane] = Wsm[(4 + (lane >> 3)) * kPs + (lane & 7)];
+    } else {
+      // =================== tile warps ===========================================================================
+      double ct[kTilesPerWarp][2];
+#pragma unroll
+      for (int t = 0; t < kTilesPerWarp; ++t) {
+        const int x = c_px[t * 8 + warp], y = c_py[t * 8 + warp];   // x <= y: initial window holds tile (y, x)
+        ct[t][0] = ct[t][1] = 0.0;
+        if (y < NT8) load_tile(y, x, ct[t][0], ct[t][1]);
       }
-      {
-        const double wb0 = Wsm[g * kPs + q], wb1 = Wsm[g * kPs + 4 + q];   // B[k][n] = W[n][k], n = g, k = 4s + q
-        const double zq0 = zJ[2 * q], zq1 = zJ[2 * q + 1];
-        const int lo = g * kPs + 2 * q;
-        const int src0 = (lane & ~3) | (q >> 1), src1 = src0 + 2;
-        const int cJ = 8 * J + 2 * q;
-        const int an = J + 16;
-        double p[2][2], part[2];
-        int xo[2] = {xo0, xo1}, ag[2];
+      if (warp == 0) {                                              // tile (0,0) is tile 0 of warp 0
+        const double dmp = dd[g];
+        Dsm[g * kPs + 2 * q] = ct[0][0] + (2 * q == g ? dmp : 0.0);
+        Dsm[g * kPs + 2 * q + 1] = ct[0][1] + (2 * q + 1 == g ? dmp : 0.0);
+        bar_arrive(2, 64);
+      }
+      // The two tiles of this warp that touch the retiring position e are worked on in fixed registers
+      // (et) so that the unrolled code can interleave them; their refills (rf) are loaded during [P] and
+      // merged back into the tile registers one step later, when the loads have long landed.
+      double rf[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      unsigned pm_prev = 0;
+
+      for (int J = 0; J < NT8; ++J) {
+        const int e = J & 15;
+        const unsigned pm = tabP[e * 8 + warp], xo2 = tabX[e * 8 + warp];
+        double et[2][2];
+        {
+          int kp = 0, kc = 0;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          ag[k] = J + ((xo[k] - e) & 15);                          // global tile row held at position xo
-          // C fragment (cols 2q, 2q+1 of row g) -> A fragments (col 4s + q of row g)
-          const double v00 = __shfl_sync(0xffffffffu, et[k][0], src0), v01 = __shfl_sync(0xffffffffu, et[k][1], src0);
-          const double v10 = __shfl_sync(0xffffffffu, et[k][0], src1), v11 = __shfl_sync(0xffffffffu, et[k][1], src1);
-          const double a0 = (q & 1) ? v01 : v00, a1 = (q & 1) ? v11 : v10;
-          dmma884(p[k][0], p[k][1], a0, wb0, 0.0, 0.0);
-          dmma884(p[k][0], p[k][1], a1, wb1, p[k][0], p[k][1]);
-          part[k] = p[k][0] * zq0 + p[k][1] * zq1;                 // right-hand side: z_a -= L_aJ zJ
-          part[k] += __shfl_xor_sync(0xffffffffu, part[k], 1);
-          part[k] += __shfl_xor_sync(0xffffffffu, part[k], 2);
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const bool panel = xo[k] != e;
-          const int r = 8 * ag[k] + g;
-          if (panel) {
-            Psm[xo[k] * kTs + lo] = p[k][0]; Psm[xo[k] * kTs + lo + 1] = p[k][1];
-            Nsm[xo[k] * kTs + lo] = -p[k][0]; Nsm[xo[k] * kTs + lo + 1] = -p[k][1];
-            if (q == 0 && r < Mp) z[r] -= part[k];
-            if (r < M) {                                           // columns of tile J are < M whenever a row below is
-              double *lp = L + Sg(r, cJ);
-              if (r - cJ <= bw) lp[0] = p[k][0];
-              if (r - cJ - 1 <= bw) lp[1] = p[k][1];
+          for (int t = 0; t < kTilesPerWarp; ++t) {
+            if ((pm_prev >> t) & 1u) { ct[t][0] = kp ? rf[1][0] : rf[0][0]; ct[t][1] = kp ? rf[1][1] : rf[0][1]; ++kp; }
+            if ((pm >> t) & 1u) {
+              if (kc == 0) { et[0][0] = ct[t][0]; et[0][1] = ct[t][1]; } else { et[1][0] = ct[t][0]; et[1][1] = ct[t][1]; }
+              ++kc;
             }
           }
-          // refill: position e now stands for tile index J + 16
-          rf[k][0] = rf[k][1] = 0.0;
-          if (an < NT8) load_tile(an, panel ? ag[k] : an, rf[k][0], rf[k][1]);
         }
-      }
-      __syncthreads();
-      // ---- [U] trailing update: C_ab -= L_aJ L_bJ^T, branch-free. Operand offsets come from the step
-      //      table; the e-tiles (whose registers are stale until the refill is merged) and tiles below the
-      //      matrix read zeros. ----
-      {
-        const unsigned *tu = tabU + e * 136 + warp;
-        const double *An = Nsm + g * kPs + q, *Bp = Psm + g * kPs + q;
+        pm_prev = pm;
+        const int xo0 = xo2 & 0xff, xo1 = (xo2 >> 8) & 0xff;
+        bar_sync(3, kMmaThreads);                                  // W_J, zJ ready; every tile warp is past [U](J-1)
+        if (s_fail) { failed = true; break; }
+        // ---- [P] panel tiles: L_aJ = A_aJ W^T; both e-tiles in one straight-line block. A tile below the
+        //      matrix is all zeros and yields zeros; the diagonal tile only skips its stores. ----
+        if (warp == kMmaWarps - 1) {                                // W_J -> global for the back substitution
+          Wg[(size_t)J * 64 + lane] = Wsm[(lane >> 3) * kPs + (lane & 7)];
+          Wg[(size_t)J * 64 + 32 + lane] = Wsm[(4 + (lane >> 3)) * kPs + (lane & 7)];
+        }
+        {
+          const double wb0 = Wsm[g * kPs + q], wb1 = Wsm[g * kPs + 4 + q];   // B[k][n] = W[n][k], n = g, k = 4s + q
+          const double zq0 = zJ[2 * q], zq1 = zJ[2 * q + 1];
+          const int lo = g * kPs + 2 * q;
+          const int src0 = (lane & ~3) | (q >> 1), src1 = src0 + 2;
+          const int cJ = 8 * J + 2 * q;
+          const int an = J + 16;
+          double p[2][2], part[2];
+          int xo[2] = {xo0, xo1}, ag[2];
 #pragma unroll
-        for (int t = 0; t < kTilesPerWarp; ++t) {
-          const unsigned o = tu[t * 8];
-          const double *A = An + (o & 0xffffu), *B = Bp + (o >> 16);
-          dmma884(ct[t][0], ct[t][1], A[0], B[0], ct[t][0], ct[t][1]);
-          dmma884(ct[t][0], ct[t][1], A[4], B[4], ct[t][0], ct[t][1]);
+          for (int k = 0; k < 2; ++k) {
+            ag[k] = J + ((xo[k] - e) & 15);                        // global tile row held at position xo
+            // C fragment (cols 2q, 2q+1 of row g) -> A fragments (col 4s + q of row g)
+            const double v00 = __shfl_sync(0xffffffffu, et[k][0], src0), v01 = __shfl_sync(0xffffffffu, et[k][1], src0);
+            const double v10 = __shfl_sync(0xffffffffu, et[k][0], src1), v11 = __shfl_sync(0xffffffffu, et[k][1], src1);
+            const double a0 = (q & 1) ? v01 : v00, a1 = (q & 1) ? v11 : v10;
+            dmma884(p[k][0], p[k][1], a0, wb0, 0.0, 0.0);
+            dmma884(p[k][0], p[k][1], a1, wb1, p[k][0], p[k][1]);
+            part[k] = p[k][0] * zq0 + p[k][1] * zq1;               // right-hand side: z_a -= L_aJ zJ
+            part[k] += __shfl_xor_sync(0xffffffffu, part[k], 1);
+            part[k] += __shfl_xor_sync(0xffffffffu, part[k], 2);
+          }
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const bool panel = xo[k] != e;
+            const int r = 8 * ag[k] + g;
+            if (panel) {
+              Psm[xo[k] * kTs + lo] = p[k][0]; Psm[xo[k] * kTs + lo + 1] = p[k][1];
+              Nsm[xo[k] * kTs + lo] = -p[k][0]; Nsm[xo[k] * kTs + lo + 1] = -p[k][1];
+              if (q == 0 && r < Mp) z[r] -= part[k];
+              if (r < M) {                                         // columns of tile J are < M whenever a row below is
+                double *lp = L + Sg(r, cJ);
+                if (r - cJ <= bw) lp[0] = p[k][0];
+                if (r - cJ - 1 <= bw) lp[1] = p[k][1];
+              }
+            }
+            // refill: position e now stands for tile index J + 16
+            rf[k][0] = rf[k][1] = 0.0;
+            if (an < NT8) load_tile(an, panel ? ag[k] : an, rf[k][0], rf[k][1]);
+          }
+        }
+        bar_sync(1, 32 * kMmaWarps);                               // all panel tiles (and z updates) of column J done
+        // ---- [U] trailing update: C_ab -= L_aJ L_bJ^T, branch-free; operand offsets from the step table
+        //      (e-tiles, whose registers are stale until the refill is merged, and tiles below the matrix read
+        //      zeros). Look-ahead: the owner of tile (J+1,J+1) updates it first and hands it to the factor
+        //      warp, so that the 8x8 factorisation of the next column overlaps the rest of this update. ----
+        {
+          const unsigned *tu = tabU + e * 136 + warp;
+          const double *An = Nsm + g * kPs + q, *Bp = Psm + g * kPs + q;
+          const int en = (J + 1) & 15;
+          const bool own_next = (J + 1 < NT8) && warp == (en & 7);
+          const int tn = en >> 3;                                  // pair {en,en} is tile en/8 of warp en%8
+          if (own_next) {
+            const unsigned o = tu[tn * 8];
+            const double *A = An + (o & 0xffffu), *B = Bp + (o >> 16);
+            double c0 = tn ? ct[1][0] : ct[0][0], c1 = tn ? ct[1][1] : ct[0][1];
+            dmma884(c0, c1, A[0], B[0], c0, c1);
+            dmma884(c0, c1, A[4], B[4], c0, c1);
+            if (tn) { ct[1][0] = c0; ct[1][1] = c1; } else { ct[0][0] = c0; ct[0][1] = c1; }
+            const double dmp = dd[8 * (J + 1) + g];
+            Dsm[g * kPs + 2 * q] = c0 + (2 * q == g ? dmp : 0.0);
+            Dsm[g * kPs + 2 * q + 1] = c1 + (2 * q + 1 == g ? dmp : 0.0);
+            bar_arrive(2, 64);
+          }
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) {
+            unsigned o = tu[t * 8];
+            if (t < 2 && own_next && t == tn) o = (16u * kTs) | ((16u * kTs) << 16);    // already applied above
+            const double *A = An + (o & 0xffffu), *B = Bp + (o >> 16);
+            dmma884(ct[t][0], ct[t][1], A[0], B[0], ct[t][0], ct[t][1]);
+            dmma884(ct[t][0], ct[t][1], A[4], B[4], ct[t][0], ct[t][1]);
+          }
         }
       }
     }
