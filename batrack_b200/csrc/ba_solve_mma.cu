@@ -18,11 +18,19 @@
 // The backward substitution streams the tile rows of L back through shared memory.
 // Why fp64: the reduced system of a short window is ill-conditioned (kappa ~ 1e3..1e4); solving it in
 // fp32 puts the result at the reference's own fp32 noise floor (~1e-4), see DESIGN.md §Precision.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "ba_internal.h"
 
 namespace ba {
 
-constexpr int kMmaWarps = 8;                 // tile warps; warp 8 is the factor warp
+constexpr int kMmaWarps = 8;                 // tile warps
+// 9 hardware warps: 0..7 = tile warps (two per scheduler: the DMMAs of [U] occupy a scheduler's FP64 unit for
+// 16 cycles each, 68 per scheduler and column, and that unit is what bounds the step), 8 = factor warp.
+// (Measured alternative: factor warp alone on scheduler 0 and 3+3+2 tile warps on the others: the factorisation
+// drops to 1.8k cycles but [U] rises to 3.1k, slower overall.)
 constexpr int kMmaThreads = 32 * (kMmaWarps + 1);
 constexpr int kTilesPerWarp = 17;
 constexpr int kBackStages = 4;     // tile rows of L in flight during the back substitution
@@ -43,8 +51,9 @@ __constant__ unsigned char c_py[136] = {
     10, 11, 12, 13, 14, 15, 9, 10, 11, 12, 13, 14, 15, 10, 11, 12, 13, 14, 15, 11, 12, 13, 14, 15, 12, 13, 14, 15, 13, 14, 15, 14, 15, 15};
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b, double c0, double c1) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
-               : "=d"(d0), "=d"(d1)
+  // not volatile: pure function of its operands, so the compiler may interleave the DMMAs of independent tiles
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+      : "=d"(d0), "=d"(d1)
                : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
 
@@ -68,9 +77,20 @@ __device__ __forceinline__ void cp_async8_d(void *smem_dst, const void *gsrc) {
 
 constexpr int tri8(int a, int b) { return a * (a + 1) / 2 + b; }
 
-__global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, int allow_retry, double *__restrict__ Wg) {
+// optional phase trace (BA_TRACE=1): clock64 stamps of tile warp 0 and of the factor warp per tile column
+#define BA_TR(slot) do { if (trace && lane == 0) trace[(size_t)J * 16 + (slot)] = clock64(); } while (0)
+// the same, but the clock is read only once `dep` is available (barrier waits are deferred to the first dependent
+// instruction, so a plain clock read right after bar.sync would not see them)
+__device__ __forceinline__ long long clk_after(double dep) { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "d"(dep)); return t; }
+__device__ __forceinline__ long long clk_after(int dep) { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep)); return t; }
+#define BA_TRD(slot, dep) do { if (trace && lane == 0) trace[(size_t)J * 16 + (slot)] = clk_after(dep); } while (0)
+
+__global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, int allow_retry, double *__restrict__ Wg,
+                                                                   long long *__restrict__ trace) {
   extern __shared__ double dsm[];
-  const int tau = threadIdx.x, lane = tau & 31, warp = tau >> 5;
+  const int tau = threadIdx.x, lane = tau & 31, hw = tau >> 5;
+  const bool is_factor = hw == kMmaWarps, is_tile = hw < kMmaWarps;
+  const int warp = hw;                                              // tile warp index 0..7 (meaningful if is_tile)
   const int g = lane >> 2, q = lane & 3;
   const int M = cv.M, bw = cv.bw, ld = cv.ld, off = cv.off;
   const int NT8 = (M + 7) >> 3, Mp = NT8 * 8;
@@ -85,7 +105,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
   unsigned *tabU = reinterpret_cast<unsigned *>(Lst + kBackStages * (8 * 128 + 64));   // [16][136] operand offsets of [U]
   unsigned *tabP = tabU + 16 * 136;        // [16][8] which (two) of a warp's 17 tiles touch position e
   unsigned *tabX = tabP + 16 * 8;          // [16][8] the other position of those two tiles, 8 bits each
-  double *xs = reinterpret_cast<double *>(tabX + 16 * 8);          // [8] x_J of the back substitution
+  double *Esm = reinterpret_cast<double *>(tabX + 16 * 8);         // [8 warps][2 slots][64] next column's e-tiles
+  double *xsol = dd;                                               // solution of the back substitution (dd is dead then)
   __shared__ int s_fail, s_nan;
   const double *__restrict__ S = cv.S;
   double *__restrict__ L = cv.L;
@@ -103,7 +124,18 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
       offA = (ax > ay ? x : y) * kTs;                               // row tile = larger global index
       offB = (ax > ay ? y : x) * kTs;
     }
-    tabU[o] = offA | (offB << 16);
+    // bits 0-11 offA, 12-23 offB, 24 this pair touches e (+25: which of the warp's two), 26 it touches e+1 (+27)
+    const int w = idx & 7, en = (e + 1) & 15;
+    unsigned fl = 0;
+    int ke = 0, kn = 0;
+    for (int t2 = 0; t2 < idx / 8; ++t2) {
+      const int x2 = c_px[t2 * 8 + w], y2 = c_py[t2 * 8 + w];
+      ke += (x2 == e || y2 == e);
+      kn += (x2 == en || y2 == en);
+    }
+    if (x == e || y == e) fl |= 1u | ((unsigned)ke << 1);
+    if (x == en || y == en) fl |= 4u | ((unsigned)kn << 3);
+    tabU[o] = offA | (offB << 12) | (fl << 24);
   }
   for (int o = tau; o < 16 * 8; o += kMmaThreads) {
     const int e = o >> 3, w = o & 7;
@@ -141,9 +173,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
     if (tau == 0) { s_fail = 0; s_nan = 0; }
     __syncthreads();                                               // z, dd, tables, zero tiles visible
     bool failed = false;
-    if (warp == kMmaWarps) {
+    if (is_factor) {
       // =================== factor warp: [A] for column J while the tile warps still update column J-1 ==========
       for (int J = 0; J < NT8; ++J) {
+        BA_TR(8);
         bar_sync(2, 64);                                           // tile (J,J) (+ damping) is in Dsm, z_J is final
         // every lane factors the 8x8 block redundantly in registers (no divergence, no extra exchange)
         double a[36];
@@ -151,15 +184,30 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
         for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int j = 0; j <= i; ++j) a[tri8(i, j)] = Dsm[i * kPs + j];
+        BA_TRD(9, a[35]);
+        // Right-looking 8x8 Cholesky fused with the forward substitutions: one right-hand side per lane, same
+        // instruction stream — lanes 0..7 solve L_JJ w = e_lane (column `lane` of W = L_JJ^-1), lane 8 solves
+        // L_JJ zJ = z_J. wv[k] is formed right after pivot k, so only (one FMA + one multiply) per row sits on
+        // the dependent chain. (L_JJ itself is never needed again: the back substitution uses W_J.)
         bool ok = true;
-        double invd[8];
+        double wv[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const double piv = a[tri8(k, k)];
-          ok = ok && (piv > 0.0);                                  // potrf info != 0 (also NaN), ba.py:11
-          const bool fast = piv > 1e-30 && piv < 1e30;
-          const double inv = fast ? rsqrt64(piv) : 1.0 / sqrt(piv);
-          invd[k] = inv;
+          const float pf = (float)piv;                             // range / sign / NaN test on the fp32 copy
+          ok = ok && (pf > 0.0f);                                  // potrf info != 0 (also NaN), ba.py:11
+          const bool fast = pf > 1e-30f && pf < 1e30f;
+          double inv;
+          if (fast) {                                              // fp32 seed (~2e-7) + one Newton step -> ~6e-14
+            const double y = (double)rsqrtf(pf);
+            inv = fma(fma(-piv * y, 0.5 * y, 0.5), y, y);
+          } else {
+            inv = 1.0 / sqrt(piv);
+          }
+          double sv = lane == 8 ? z[8 * J + k] : (lane == k ? 1.0 : 0.0);
+#pragma unroll
+          for (int j = 0; j < k; ++j) sv -= a[tri8(k, j)] * wv[j];
+          wv[k] = sv * inv;
 #pragma unroll
           for (int i = k + 1; i < 8; ++i) a[tri8(i, k)] *= inv;
 #pragma unroll
@@ -168,17 +216,6 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
             for (int i = j; i < 8; ++i) a[tri8(i, j)] -= a[tri8(i, k)] * a[tri8(j, k)];
         }
         if (ok) {
-          // (L_JJ itself is never needed again: the back substitution uses W_J.)
-          // One forward substitution per lane, same instruction stream, different right-hand side:
-          // lanes 0..7 solve L_JJ w = e_lane (column `lane` of W = L_JJ^-1), lane 8 solves L_JJ zJ = z_J.
-          double wv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            double sv = lane == 8 ? z[8 * J + i] : (lane == i ? 1.0 : 0.0);
-#pragma unroll
-            for (int j = 0; j < i; ++j) sv -= a[tri8(i, j)] * wv[j];
-            wv[i] = sv * invd[i];
-          }
           if (lane < 8) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) Wsm[i * kPs + lane] = wv[i];
@@ -189,10 +226,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
         } else if (lane == 0) {
           s_fail = 1;
         }
-        bar_arrive(3, kMmaThreads);                                // W_J, zJ (or the failure flag) published
+        BA_TR(10);
+        bar_arrive(3, 32 * (kMmaWarps + 1));                       // W_J, zJ (or the failure flag) published
         if (!ok) { failed = true; break; }
       }
-    } else {
+    } else if (is_tile) {
       // =================== tile warps ===========================================================================
       double ct[kTilesPerWarp][2];
 #pragma unroll
@@ -201,37 +239,49 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
         ct[t][0] = ct[t][1] = 0.0;
         if (y < NT8) load_tile(y, x, ct[t][0], ct[t][1]);
       }
-      if (warp == 0) {                                              // tile (0,0) is tile 0 of warp 0
+      double *myE = Esm + warp * 128 + 2 * lane;                    // this warp's two e-tile slots (fragment layout)
+      {                                                             // e-tiles of column 0 = "next" tiles of position 15
+        const unsigned *tu = tabU + 15 * 136 + warp;
+#pragma unroll
+        for (int t = 0; t < kTilesPerWarp; ++t) {
+          const unsigned o = tu[t * 8];
+          if (o & (4u << 24)) { double *d = myE + ((o >> 27) & 1u) * 64; d[0] = ct[t][0]; d[1] = ct[t][1]; }
+        }
+      }
+      if (warp == 0) {                                              // tile (0,0) is tile 0 of tile warp 0
         const double dmp = dd[g];
         Dsm[g * kPs + 2 * q] = ct[0][0] + (2 * q == g ? dmp : 0.0);
         Dsm[g * kPs + 2 * q + 1] = ct[0][1] + (2 * q + 1 == g ? dmp : 0.0);
         bar_arrive(2, 64);
       }
-      // The two tiles of this warp that touch the retiring position e are worked on in fixed registers
-      // (et) so that the unrolled code can interleave them; their refills (rf) are loaded during [P] and
-      // merged back into the tile registers one step later, when the loads have long landed.
-      double rf[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-      unsigned pm_prev = 0;
-
+      __syncwarp();
+      // Per column J, the two tiles of this warp that touch the retiring position e ("e-tiles") are read from
+      // the warp's shared slots (written by the previous [U]) into fixed registers, so the unrolled code never
+      // indexes the tile registers dynamically. Their refills are loaded into fixed registers at the top of the
+      // step and moved into the tile registers by predicated moves inside the [U] loop.
       for (int J = 0; J < NT8; ++J) {
         const int e = J & 15;
-        const unsigned pm = tabP[e * 8 + warp], xo2 = tabX[e * 8 + warp];
-        double et[2][2];
+        const unsigned xo2 = tabX[e * 8 + warp];
+        const int xo0 = xo2 & 0xff, xo1 = (xo2 >> 8) & 0xff;
+        if (warp == 0) BA_TR(0);
+        double et[2][2], rf[2][2];
+        et[0][0] = myE[0]; et[0][1] = myE[1]; et[1][0] = myE[64]; et[1][1] = myE[65];
+        int ag[2];
         {
-          int kp = 0, kc = 0;
+          const int an = J + 16;
+          const int xo[2] = {xo0, xo1};
 #pragma unroll
-          for (int t = 0; t < kTilesPerWarp; ++t) {
-            if ((pm_prev >> t) & 1u) { ct[t][0] = kp ? rf[1][0] : rf[0][0]; ct[t][1] = kp ? rf[1][1] : rf[0][1]; ++kp; }
-            if ((pm >> t) & 1u) {
-              if (kc == 0) { et[0][0] = ct[t][0]; et[0][1] = ct[t][1]; } else { et[1][0] = ct[t][0]; et[1][1] = ct[t][1]; }
-              ++kc;
-            }
+          for (int k = 0; k < 2; ++k) {
+            ag[k] = J + ((xo[k] - e) & 15);                        // global tile row held at the other position
+            rf[k][0] = rf[k][1] = 0.0;                             // position e next stands for tile index J + 16
+            if (an < NT8) load_tile(an, xo[k] == e ? an : ag[k], rf[k][0], rf[k][1]);
           }
         }
-        pm_prev = pm;
-        const int xo0 = xo2 & 0xff, xo1 = (xo2 >> 8) & 0xff;
-        bar_sync(3, kMmaThreads);                                  // W_J, zJ ready; every tile warp is past [U](J-1)
-        if (s_fail) { failed = true; break; }
+        if (warp == 0) BA_TR(1);
+        bar_sync(3, 32 * (kMmaWarps + 1));                         // W_J, zJ ready; every tile warp is past [U](J-1)
+        const int sf = s_fail;
+        if (warp == 0) BA_TRD(2, sf);
+        if (sf) { failed = true; break; }
         // ---- [P] panel tiles: L_aJ = A_aJ W^T; both e-tiles in one straight-line block. A tile below the
         //      matrix is all zeros and yields zeros; the diagonal tile only skips its stores. ----
         if (warp == kMmaWarps - 1) {                                // W_J -> global for the back substitution
@@ -244,12 +294,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
           const int lo = g * kPs + 2 * q;
           const int src0 = (lane & ~3) | (q >> 1), src1 = src0 + 2;
           const int cJ = 8 * J + 2 * q;
-          const int an = J + 16;
           double p[2][2], part[2];
-          int xo[2] = {xo0, xo1}, ag[2];
+          const int xo[2] = {xo0, xo1};
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            ag[k] = J + ((xo[k] - e) & 15);                        // global tile row held at position xo
             // C fragment (cols 2q, 2q+1 of row g) -> A fragments (col 4s + q of row g)
             const double v00 = __shfl_sync(0xffffffffu, et[k][0], src0), v01 = __shfl_sync(0xffffffffu, et[k][1], src0);
             const double v10 = __shfl_sync(0xffffffffu, et[k][0], src1), v11 = __shfl_sync(0xffffffffu, et[k][1], src1);
@@ -262,9 +310,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
           }
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            const bool panel = xo[k] != e;
             const int r = 8 * ag[k] + g;
-            if (panel) {
+            if (xo[k] != e) {
               Psm[xo[k] * kTs + lo] = p[k][0]; Psm[xo[k] * kTs + lo + 1] = p[k][1];
               Nsm[xo[k] * kTs + lo] = -p[k][0]; Nsm[xo[k] * kTs + lo + 1] = -p[k][1];
               if (q == 0 && r < Mp) z[r] -= part[k];
@@ -274,25 +321,25 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
                 if (r - cJ - 1 <= bw) lp[1] = p[k][1];
               }
             }
-            // refill: position e now stands for tile index J + 16
-            rf[k][0] = rf[k][1] = 0.0;
-            if (an < NT8) load_tile(an, panel ? ag[k] : an, rf[k][0], rf[k][1]);
           }
         }
+        if (warp == 0) BA_TR(3);
         bar_sync(1, 32 * kMmaWarps);                               // all panel tiles (and z updates) of column J done
-        // ---- [U] trailing update: C_ab -= L_aJ L_bJ^T, branch-free; operand offsets from the step table
-        //      (e-tiles, whose registers are stale until the refill is merged, and tiles below the matrix read
-        //      zeros). Look-ahead: the owner of tile (J+1,J+1) updates it first and hands it to the factor
-        //      warp, so that the 8x8 factorisation of the next column overlaps the rest of this update. ----
+        if (warp == 0) BA_TRD(4, Psm[16 * kTs]);
+        // ---- [U] trailing update: C_ab -= L_aJ L_bJ^T, branch-free; operand offsets and flags from the step
+        //      table (e-tiles and tiles below the matrix read zeros). Look-ahead: the owner of tile (J+1,J+1)
+        //      updates it first and hands it to the factor warp, so that the 8x8 factorisation of the next column
+        //      overlaps the rest of this update. Inside the loop, an e-tile takes its refill, and a tile that
+        //      touches position e+1 is copied to the warp's shared slots for the next column. ----
         {
           const unsigned *tu = tabU + e * 136 + warp;
           const double *An = Nsm + g * kPs + q, *Bp = Psm + g * kPs + q;
           const int en = (J + 1) & 15;
           const bool own_next = (J + 1 < NT8) && warp == (en & 7);
-          const int tn = en >> 3;                                  // pair {en,en} is tile en/8 of warp en%8
+          const int tn = en >> 3;                                  // pair {en,en} is tile en/8 of tile warp en%8
           if (own_next) {
             const unsigned o = tu[tn * 8];
-            const double *A = An + (o & 0xffffu), *B = Bp + (o >> 16);
+            const double *A = An + (o & 0xfffu), *B = Bp + ((o >> 12) & 0xfffu);
             double c0 = tn ? ct[1][0] : ct[0][0], c1 = tn ? ct[1][1] : ct[0][1];
             dmma884(c0, c1, A[0], B[0], c0, c1);
             dmma884(c0, c1, A[4], B[4], c0, c1);
@@ -302,15 +349,33 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
             Dsm[g * kPs + 2 * q + 1] = c1 + (2 * q + 1 == g ? dmp : 0.0);
             bar_arrive(2, 64);
           }
+          unsigned ot[kTilesPerWarp];
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) ot[t] = tu[t * 8];
+          {                                                         // the look-ahead tile was already updated above
+            const unsigned zo = (16u * kTs) | ((16u * kTs) << 12);
+            if (own_next && tn == 0) ot[0] = (ot[0] & 0xff000000u) | zo;
+            if (own_next && tn == 1) ot[1] = (ot[1] & 0xff000000u) | zo;
+          }
 #pragma unroll
           for (int t = 0; t < kTilesPerWarp; ++t) {
-            unsigned o = tu[t * 8];
-            if (t < 2 && own_next && t == tn) o = (16u * kTs) | ((16u * kTs) << 16);    // already applied above
-            const double *A = An + (o & 0xffffu), *B = Bp + (o >> 16);
+            const unsigned o = ot[t];
+            const double *A = An + (o & 0xfffu), *B = Bp + ((o >> 12) & 0xfffu);
             dmma884(ct[t][0], ct[t][1], A[0], B[0], ct[t][0], ct[t][1]);
             dmma884(ct[t][0], ct[t][1], A[4], B[4], ct[t][0], ct[t][1]);
           }
+          // an e-tile's registers take its refill; a tile that touches position e+1 goes to the warp's slots
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) {
+            const unsigned fl = ot[t] >> 24;
+            const bool ise = fl & 1u, sel = fl & 2u;
+            ct[t][0] = ise ? (sel ? rf[1][0] : rf[0][0]) : ct[t][0];
+            ct[t][1] = ise ? (sel ? rf[1][1] : rf[0][1]) : ct[t][1];
+            if (fl & 4u) { double *d = myE + ((fl >> 3) & 1u) * 64; d[0] = ct[t][0]; d[1] = ct[t][1]; }
+          }
         }
+        if (warp == 0) BA_TR(5);
+        __syncwarp();                                              // slots written by this warp, read by it next step
       }
     }
     __syncthreads();
@@ -349,32 +414,37 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
       else asm volatile("cp.async.commit_group;" ::: "memory");
       const double *st = Lst + (size_t)(J % kBackStages) * (8 * 128 + 64);
       const double *Wj = st + 8 * 128;                             // W_J row-major 8x8
-      // x_J = W_J^T z_J : 8 threads, one component each (two partial sums to halve the FMA chain)
-      if (tau < 8) {
-        double s0 = 0.0, s1 = 0.0;
+      // x_J = W_J^T z_J, computed redundantly by every thread that uses it (broadcast loads, no exchange, one
+      // barrier per tile row); the solution goes to xsol so that z_J stays readable during the iteration.
+      if (tau < 32 + 120) {
+        double zz[8], xJ[8];
 #pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-          s0 += (k >= tau ? Wj[k * 8 + tau] : 0.0) * z[8 * J + k];
-          s1 += (k + 1 >= tau ? Wj[(k + 1) * 8 + tau] : 0.0) * z[8 * J + k + 1];
-        }
-        __syncwarp(0xffu);                                         // all 8 lanes have read z_J
-        xs[tau] = s0 + s1;
-        z[8 * J + tau] = s0 + s1;
-      }
-      __syncthreads();
-      if (tau >= 32 && tau < 32 + 120) {
-        const int xcol = tau - 32, c = 8 * (J - 15) + xcol;
-        if (c >= 0) {
+        for (int k = 0; k < 8; ++k) zz[k] = z[8 * J + k];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
           double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-          for (int gg = 0; gg < 8; gg += 2) { s0 += st[gg * 128 + xcol] * xs[gg]; s1 += st[(gg + 1) * 128 + xcol] * xs[gg + 1]; }
-          z[c] -= s0 + s1;
+          for (int k = i; k < 8; k += 2) { s0 += Wj[k * 8 + i] * zz[k]; if (k + 1 < 8) s1 += Wj[(k + 1) * 8 + i] * zz[k + 1]; }
+          xJ[i] = s0 + s1;
+        }
+        if (tau == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xsol[8 * J + i] = xJ[i];
+        }
+        if (tau >= 32) {
+          const int xcol = tau - 32, c = 8 * (J - 15) + xcol;
+          if (c >= 0) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int gg = 0; gg < 8; gg += 2) { s0 += st[gg * 128 + xcol] * xJ[gg]; s1 += st[(gg + 1) * 128 + xcol] * xJ[gg + 1]; }
+            z[c] -= s0 + s1;
+          }
         }
       }
     }
     __syncthreads();
     int nan_local = 0;
-    for (int r = tau; r < M; r += kMmaThreads) { const double v = z[r]; cv.dX[r] = v; nan_local |= (v != v); }
+    for (int r = tau; r < M; r += kMmaThreads) { const double v = xsol[r]; cv.dX[r] = v; nan_local |= (v != v); }
     if (nan_local) s_nan = 1;
     __syncthreads();
     if (s_nan && allow_retry && attempt == 0) { status |= 2; __syncthreads(); continue; }   // ba.py:324-325
@@ -385,18 +455,38 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
 
 size_t solve_mma_smem_bytes(int M) {
   const int Mp = ((M + 7) / 8) * 8;
-  return ((size_t)2 * Mp + 2 * 17 * kTs + 2 * kTs + 8 + kBackStages * (8 * 128 + 64)) * sizeof(double) +
-         (16 * 136 + 2 * 16 * 8) * sizeof(unsigned) + 8 * sizeof(double);
+  return ((size_t)2 * Mp + 8 * 2 * 64 + 2 * 17 * kTs + 2 * kTs + 8 + kBackStages * (8 * 128 + 64)) * sizeof(double) +
+         (16 * 136 + 2 * 16 * 8) * sizeof(unsigned);
 }
 
 int launch_solve_band_mma(const CallView &cv, int allow_retry, double *Wg, cudaStream_t s) {
   static bool attr_set = false;
+  static long long *trace = nullptr;
+  static int trace_left = 0;
   if (!attr_set) {
     BA_CUDA(cudaFuncSetAttribute(k_solve_band_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
+    if (const char *e = getenv("BA_TRACE")) { trace_left = atoi(e); BA_CUDA(cudaMalloc(&trace, 16 * 8 * 4096)); }
     attr_set = true;
   }
-  k_solve_band_mma<<<1, kMmaThreads, solve_mma_smem_bytes(cv.M), s>>>(cv, allow_retry, Wg);
+  const bool tr = trace && trace_left > 0 && (cv.M + 7) / 8 <= 4096;
+  k_solve_band_mma<<<1, kMmaThreads, solve_mma_smem_bytes(cv.M), s>>>(cv, allow_retry, Wg, tr ? trace : nullptr);
   BA_LAUNCH_CHECK();
+  if (tr && --trace_left == 0) {       // debug only: synchronises and prints mean phase lengths in SM cycles
+    const int nt = (cv.M + 7) / 8;
+    std::vector<long long> h((size_t)nt * 16);
+    BA_CUDA(cudaStreamSynchronize(s));
+    BA_CUDA(cudaMemcpy(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost));
+    double d[8] = {0};
+    for (int J = 1; J + 1 < nt; ++J) {
+      const long long *a = &h[(size_t)J * 16], *n = &h[(size_t)(J + 1) * 16];
+      d[0] += a[1] - a[0]; d[1] += a[2] - a[1]; d[2] += a[3] - a[2]; d[3] += a[4] - a[3]; d[4] += a[5] - a[4];
+      d[5] += n[0] - a[5]; d[6] += a[9] - a[8]; d[7] += a[10] - a[9];
+    }
+    const double k = nt - 2;
+    fprintf(stderr, "[BA_TRACE] tiles %d | tile warp 0: extract %.0f waitW %.0f P %.0f waitP %.0f U %.0f refill %.0f | "
+            "factor warp: waitD %.0f A %.0f | step %.0f cycles\n", nt, d[0] / k, d[1] / k, d[2] / k, d[3] / k, d[4] / k,
+            d[5] / k, d[6] / k, d[7] / k, (double)(h[(size_t)(nt - 1) * 16] - h[16]) / k);
+  }
   return BA_OK;
 }
 
