@@ -423,9 +423,11 @@ __global__ void k_track_q(PlanView pv, CallView cv) {
 // =================================================================================================
 constexpr int kSchurRun = 8;
 
-__global__ void __launch_bounds__(kSchurThreads) k_schur(PlanView pv, CallView cv, int tile_tracks) {
+constexpr int kSchurStages = 3;   // sub-tiles of E rows in flight (cp.async ring)
+
+__global__ void __launch_bounds__(kSchurThreads, 2) k_schur(PlanView pv, CallView cv, int tile_tracks) {
   constexpr int NT = kSchurThreads;
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int tau = threadIdx.x;
   const int u = blockIdx.x;
   const int g = pv.u_grp[u];
@@ -435,10 +437,22 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(PlanView pv, CallView c
   const int rowlen = 6 * W;
   const int *slot_pose = pv.slot_pose + 2 * pv.g_pat[g];
   const float *Erows = cv.Est + pv.g_eoff[g];
-  float *Es = smem;                               // [tile_tracks][rowlen]
-  float *qs = smem + (size_t)tile_tracks * rowlen; // [tile_tracks] Q_k
-  float *qws = qs + tile_tracks;                  // [tile_tracks] Q_k w_k
+  const int stage_floats = tile_tracks * (rowlen + 2);            // [tile][rowlen] E rows + [tile] float2 (Q, w)
   const int npairs = W * (W + 1) / 2;
+  const int nst = (t1 - t0 + tile_tracks - 1) / tile_tracks;
+
+  // stage st <- E rows and (Q, w) of tracks [t0 + st*tile, ...): one contiguous 8-byte-aligned slab each
+  auto issue = [&](int st) {
+    if (st < nst) {
+      const int tt = t0 + st * tile_tracks, nt = min(tile_tracks, t1 - tt);
+      float *dst = smem + (size_t)(st % kSchurStages) * stage_floats;
+      const float2 *src = reinterpret_cast<const float2 *>(Erows + (size_t)(tt - gt0) * rowlen);
+      for (int o = tau; o < nt * rowlen / 2; o += NT) cp_async8(reinterpret_cast<float2 *>(dst) + o, src + o);
+      float2 *dq = reinterpret_cast<float2 *>(dst + (size_t)tile_tracks * rowlen);
+      for (int o = tau; o < nt; o += NT) cp_async8(dq + o, cv.Qw + tt + o);
+    }
+    cp_async_commit();
+  };
 
   for (int pb = 0; pb < npairs; pb += NT) {
     const int x = pb + tau;
@@ -454,18 +468,22 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(PlanView pv, CallView c
 #pragma unroll
     for (int k = 0; k < 36; ++k) acc[k] = 0.0;
 
-    for (int tt = t0; tt < t1; tt += tile_tracks) {
-      const int nt = min(tile_tracks, t1 - tt);
-      const float *src = Erows + (size_t)(tt - gt0) * rowlen;
-      for (int o = tau; o < nt * rowlen; o += NT) Es[o] = src[o];
-      for (int o = tau; o < nt; o += NT) { const float2 qw = cv.Qw[tt + o]; qs[o] = qw.x; qws[o] = qw.x * qw.y; }
-      __syncthreads();
+    __syncthreads();                               // ring free (previous pair batch done)
+    issue(0);
+    issue(1);
+    for (int st = 0; st < nst; ++st) {
+      cp_async_wait<1>();
+      __syncthreads();                             // stage st landed for everyone; stage st-1 fully consumed
+      issue(st + 2);
+      const int nt = min(tile_tracks, t1 - (t0 + st * tile_tracks));
+      const float *Es = smem + (size_t)(st % kSchurStages) * stage_floats;
+      const float2 *qw = reinterpret_cast<const float2 *>(Es + (size_t)tile_tracks * rowlen);
       if (pb == 0) {                              // y -= E Q w   (ba.py:322)
         for (int r = tau; r < rowlen; r += NT) {
           const int pose = slot_pose[r / 6];
           if (pose_free(pose, cv)) {
             double s = 0.0;
-            for (int k = 0; k < nt; ++k) s += (double)(qws[k] * Es[k * rowlen + r]);
+            for (int k = 0; k < nt; ++k) s += (double)(qw[k].x * qw[k].y * Es[k * rowlen + r]);
             red_add(cv.y + 6 * (pose - cv.fixedp) + (r % 6), -s);
           }
         }
@@ -477,11 +495,12 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(PlanView pv, CallView c
           for (int k = 0; k < 36; ++k) part[k] = 0.0f;
           const int k1 = min(k0 + kSchurRun, nt);
           for (int k = k0; k < k1; ++k) {
-            const float q = qs[k];
-            const float *ea = Es + k * rowlen + 6 * a, *eb = Es + k * rowlen + 6 * b;
-            float va[6], vb[6];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) { va[c] = q * ea[c]; vb[c] = eb[c]; }
+            const float q = qw[k].x;
+            const float2 *ea = reinterpret_cast<const float2 *>(Es + k * rowlen + 6 * a);
+            const float2 *eb = reinterpret_cast<const float2 *>(Es + k * rowlen + 6 * b);
+            const float2 a01 = ea[0], a23 = ea[1], a45 = ea[2], b01 = eb[0], b23 = eb[1], b45 = eb[2];
+            const float va[6] = {q * a01.x, q * a01.y, q * a23.x, q * a23.y, q * a45.x, q * a45.y};
+            const float vb[6] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
 #pragma unroll
             for (int c = 0; c < 6; ++c)
 #pragma unroll
@@ -491,7 +510,6 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur(PlanView pv, CallView c
           for (int k = 0; k < 36; ++k) acc[k] += (double)part[k];
         }
       }
-      __syncthreads();
     }
     if (have) {                                   // S -= (E Q) E^T   (ba.py:321), lower storage only
       const int pa = slot_pose[a], pb2 = slot_pose[b];          // pa >= pb2 (slots ascend by pose)
@@ -871,9 +889,9 @@ extern "C" int ba_assemble(BaPlan *pl, const BaProblem *pb, void *stream_) {
   BA_MARK(pl, BA_STAGE_SCHUR, s);
   if (!so) {
     const int rowmax = 6 * pl->info.max_slots;
-    int tile = (int)((64 * 1024 / sizeof(float)) / (rowmax + 2));
-    tile = tile < 1 ? 1 : (tile > 128 ? 128 : tile);
-    const size_t smem = (size_t)tile * (rowmax + 2) * sizeof(float);
+    int tile = (int)((24 * 1024 / sizeof(float)) / (rowmax + 2));       // per stage; kSchurStages stages in flight
+    tile = tile < 1 ? 1 : (tile > 32 ? 32 : tile);
+    const size_t smem = (size_t)kSchurStages * tile * (rowmax + 2) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
       BA_CUDA(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

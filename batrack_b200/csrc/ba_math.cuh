@@ -158,10 +158,20 @@ struct EdgeTerms {
   float valid;
 };
 
+// fast reciprocal / reciprocal square root on the device (a few ulp; the per-edge terms are fp32 anyway and
+// parity is judged at 1e-4 against fp64), exact forms on the host
+#ifdef __CUDA_ARCH__
+BA_HD float ba_rcp(float x) { return __frcp_rn(x); }
+BA_HD float ba_rsqrt(float x) { return rsqrtf(x); }
+#else
+BA_HD float ba_rcp(float x) { return 1.0f / x; }
+BA_HD float ba_rsqrt(float x) { return 1.0f / sqrtf(x); }
+#endif
+
 BA_HD float robust_weight(float r, int loss) {        // ba.py:81-100
   float s = r * r;
-  if (loss == 1) return s > 1.0f ? 1.0f / sqrtf(s) : 1.0f;
-  if (loss == 2) return 1.0f / (1.0f + s);
+  if (loss == 1) return s > 1.0f ? ba_rsqrt(s) : 1.0f;   // huber: 1/|r|
+  if (loss == 2) return ba_rcp(1.0f + s);
   return 1.0f;
 }
 
@@ -177,11 +187,11 @@ BA_HD void edge_terms(const PairConst &c, float ifxi, float ifyi, float px, floa
   float Z = c.R[6] * x0 + c.R[7] * y0 + c.R[8] + c.t.z * pd;
   float H = pd;
   // proj (projective_ops.py:43-45)
-  float dc = 1.0f / fmaxf(Z, 1e-2f);
+  float dc = ba_rcp(fmaxf(Z, 1e-2f));
   o.u = c.fxj * (dc * X) + c.cxj;
   o.v = c.fyj * (dc * Y) + c.cyj;
   // Jacobians (projective_ops.py:80-98)
-  float dj = fabsf(Z) > kMinDepth ? 1.0f / Z : 0.0f;
+  float dj = fabsf(Z) > kMinDepth ? ba_rcp(Z) : 0.0f;
   float a = c.fxj * dj, b = -c.fxj * X * dj * dj;
   float cc = c.fyj * dj, e = -c.fyj * Y * dj * dj;
   o.Jj0[0] = a * H; o.Jj0[1] = 0.0f;   o.Jj0[2] = b * H; o.Jj0[3] = b * Y;           o.Jj0[4] = a * Z - b * X; o.Jj0[5] = -a * Y;
@@ -191,7 +201,7 @@ BA_HD void edge_terms(const PairConst &c, float ifxi, float ifyi, float px, floa
   // residual + validity (ba.py:226-242, projective_ops.py:100)
   float r0 = tx - o.u, r1 = ty - o.v;
   bool ok = Z > kMinDepth;
-  ok = ok && (sqrtf(r0 * r0 + r1 * r1) < 250.0f);
+  ok = ok && (r0 * r0 + r1 * r1 < 250.0f * 250.0f);      // ||r|| < 250
   ok = ok && (o.u > bounds[0]) && (o.v > bounds[1]) && (o.u < bounds[2]) && (o.v < bounds[3]);
   o.valid = ok ? 1.0f : 0.0f;
   o.w0 = ok ? wx * robust_weight(r0, loss) : 0.0f;
