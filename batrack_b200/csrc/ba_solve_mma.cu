@@ -67,7 +67,8 @@ __device__ __forceinline__ double rsqrt64(double x) {
 }
 
 // named barriers (id 0 is __syncthreads): 1 = panel tiles complete (tile warps), 2 = diagonal tile published
-// (owner warp -> factor warp), 3 = W_J / zJ ready (factor warp -> tile warps; also closes the previous [U])
+// (owner warp -> factor warp), 3 = W_J / zJ ready (factor warp -> tile warps; also closes the previous [U]),
+// 4 = panel tile L_{J+1,J} stored (its producer -> owner of tile (J+1,J+1))
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -323,32 +324,38 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
             }
           }
         }
+        // ---- look-ahead: tile (J+1,J+1) only needs L_{J+1,J}. The warp that produced that panel tile signals
+        //      the owner of (J+1,J+1) directly (barrier 4), which updates its tile, adds the damping and hands it
+        //      to the factor warp (barrier 2) — the 8x8 factorisation of column J+1 then overlaps the rest of
+        //      [P] and all of [U] of column J. ----
+        const unsigned *tu = tabU + e * 136 + warp;
+        const double *An = Nsm + g * kPs + q, *Bp = Psm + g * kPs + q;
+        const int en = (J + 1) & 15;
+        const bool have_next = J + 1 < NT8;
+        const bool own_next = have_next && warp == (en & 7);
+        const bool is_prod = have_next && (xo0 == en || xo1 == en);
+        const int tn = en >> 3;                                    // pair {en,en} is tile en/8 of tile warp en%8
+        if (is_prod && !own_next) bar_arrive(4, 64);
+        if (own_next) {
+          if (is_prod) __syncwarp(); else bar_sync(4, 64);
+          const unsigned o = tu[tn * 8];
+          const double *A = An + (o & 0xfffu), *B = Bp + ((o >> 12) & 0xfffu);
+          double c0 = tn ? ct[1][0] : ct[0][0], c1 = tn ? ct[1][1] : ct[0][1];
+          dmma884(c0, c1, A[0], B[0], c0, c1);
+          dmma884(c0, c1, A[4], B[4], c0, c1);
+          if (tn) { ct[1][0] = c0; ct[1][1] = c1; } else { ct[0][0] = c0; ct[0][1] = c1; }
+          const double dmp = dd[8 * (J + 1) + g];
+          Dsm[g * kPs + 2 * q] = c0 + (2 * q == g ? dmp : 0.0);
+          Dsm[g * kPs + 2 * q + 1] = c1 + (2 * q + 1 == g ? dmp : 0.0);
+          bar_arrive(2, 64);
+        }
         if (warp == 0) BA_TR(3);
         bar_sync(1, 32 * kMmaWarps);                               // all panel tiles (and z updates) of column J done
         if (warp == 0) BA_TRD(4, Psm[16 * kTs]);
         // ---- [U] trailing update: C_ab -= L_aJ L_bJ^T, branch-free; operand offsets and flags from the step
-        //      table (e-tiles and tiles below the matrix read zeros). Look-ahead: the owner of tile (J+1,J+1)
-        //      updates it first and hands it to the factor warp, so that the 8x8 factorisation of the next column
-        //      overlaps the rest of this update. Inside the loop, an e-tile takes its refill, and a tile that
-        //      touches position e+1 is copied to the warp's shared slots for the next column. ----
+        //      table (e-tiles and tiles below the matrix read zeros). Inside the loop, an e-tile takes its refill,
+        //      and a tile that touches position e+1 is copied to the warp's shared slots for the next column. ----
         {
-          const unsigned *tu = tabU + e * 136 + warp;
-          const double *An = Nsm + g * kPs + q, *Bp = Psm + g * kPs + q;
-          const int en = (J + 1) & 15;
-          const bool own_next = (J + 1 < NT8) && warp == (en & 7);
-          const int tn = en >> 3;                                  // pair {en,en} is tile en/8 of tile warp en%8
-          if (own_next) {
-            const unsigned o = tu[tn * 8];
-            const double *A = An + (o & 0xfffu), *B = Bp + ((o >> 12) & 0xfffu);
-            double c0 = tn ? ct[1][0] : ct[0][0], c1 = tn ? ct[1][1] : ct[0][1];
-            dmma884(c0, c1, A[0], B[0], c0, c1);
-            dmma884(c0, c1, A[4], B[4], c0, c1);
-            if (tn) { ct[1][0] = c0; ct[1][1] = c1; } else { ct[0][0] = c0; ct[0][1] = c1; }
-            const double dmp = dd[8 * (J + 1) + g];
-            Dsm[g * kPs + 2 * q] = c0 + (2 * q == g ? dmp : 0.0);
-            Dsm[g * kPs + 2 * q + 1] = c1 + (2 * q + 1 == g ? dmp : 0.0);
-            bar_arrive(2, 64);
-          }
           unsigned ot[kTilesPerWarp];
 #pragma unroll
           for (int t = 0; t < kTilesPerWarp; ++t) ot[t] = tu[t * 8];
