@@ -15,6 +15,16 @@ constexpr int kSchurThreads = 256;    // CTA size of the per-track Schur kernel
 constexpr int kSolveThreads = 1024;   // CTA size of the window Cholesky
 constexpr int kMaxWindow = 150;       // largest band window (bw + 1) the shared-memory solver holds (fp64)
 
+// Everything the edge pass needs to know about one chunk, gathered at plan time so that a CTA starts with
+// one 48-byte load instead of a chain of dependent index loads.
+struct ChunkDesc {
+  int g, t0, t1, gt0;      // group, track range, first track of the group
+  int pat0, d, W, ebase;   // pattern offset, degree, slots, first sorted edge of the group
+  int nm, R, pad0, pad1;   // multi slots, staged items per track
+  long long eoff;          // offset of the group's E rows
+  long long pad2;
+};
+
 // Device-side view of the cached topology (all pointers device memory owned by the plan).
 struct PlanView {
   int64_t E;
@@ -42,6 +52,7 @@ struct PlanView {
   int dmax;                // longest track
   const int *c_t0, *c_grp; // [n_chunks+1], [n_chunks]  edge-pass work units (track ranges)
   const int *u_t0, *u_grp; // [n_units+1],  [n_units]   Schur work units
+  const ChunkDesc *cdesc;  // [n_chunks]
 };
 
 // Per-call view: problem pointers + the layout of the reduced system for this fixedp.

@@ -49,7 +49,7 @@ __device__ __forceinline__ double *S_at(const CallView &c, int r, int col) {
 // =================================================================================================
 constexpr int kAccComps = 27;     // per-thread accumulators: Bjj lower[21] vj[6]
 constexpr int kPosFloats = 20;    // per-position constants: R[9] t[3] 1/fxi 1/fyi cxi cyi fxj fyj cxj cyj
-constexpr int kFlushPos = 32;     // positions flushed per round
+constexpr int kFlushPos = 24;     // positions flushed per round (27+36+90 doubles each in the dead prefetch buffers)
 constexpr int kFlushOuts = 90;    // Bjj[21] Bii[21] Bij[36] vj[6] vi[6]
 constexpr int kStagePasses = 4;   // passes whose targets / weights are prefetched together (2 stages in flight)
 constexpr size_t kEdgeSmemBytes = (size_t)(kAccComps + kPosFloats + 3) * kEdgeThreads * sizeof(float) +
@@ -76,23 +76,18 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
   float *spatch = shc + kPosFloats * NT;                // [3 NT]  (x, y, inverse depth) of the chunk's tracks
   float2 *sin = reinterpret_cast<float2 *>(spatch + 3 * NT);   // [2 stages][kStagePasses][2][NT] target / weight
   const int tau = threadIdx.x;
-  const int chunk = blockIdx.x;
-  const int g = pv.c_grp[chunk];
-  const int pat0 = pv.g_pat[g];
-  const int d = pv.g_pat[g + 1] - pat0;
+  const ChunkDesc cd = pv.cdesc[blockIdx.x];
+  const int g = cd.g, pat0 = cd.pat0, d = cd.d;
   if (d > NT) return;                                   // long tracks: k_edge_pass_long
-  const int t0 = pv.c_t0[chunk], t1 = pv.c_t0[chunk + 1];
-  const int gt0 = pv.g_t0[g];
-  const int W = pv.g_W[g];
-  const int ebase = pv.tptr[gt0];
+  const int t0 = cd.t0, t1 = cd.t1, gt0 = cd.gt0, W = cd.W, ebase = cd.ebase;
   const int sbase = 2 * pat0;
   const int *slot_pose = pv.slot_pose + sbase;
-  float *Erows = cv.Est + pv.g_eoff[g];
+  float *Erows = cv.Est + cd.eoff;
   const int rowlen = 6 * W;
-  const int nm = pv.g_nm[g];
+  const int nm = cd.nm;
   const int *ms_ptr = pv.ms_ptr + sbase + g;
   const int *ms_slot = pv.ms_slot + sbase;
-  const int R = ms_ptr[nm];                             // staged (multi-slot) items per track
+  const int R = cd.R;                                   // staged (multi-slot) items per track
   const int Tp = NT / d;                                // tracks per pass
   const bool active = tau < Tp * d;
   const int kappa = tau / d;
@@ -242,50 +237,65 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
   }
 
   if (!STRUCT_ONLY) {
-    // ---- flush: reduce Bjj / vj over kappa (fp64), map to the i side, scatter with fp64 atomics ----
+    // ---- flush: reduce Bjj / vj over kappa (fp64), map to the i side, scatter with fp64 atomics. Every phase is
+    //      spread over the CTA: (position, component) sums, (position, column) products A Bjj, (position, row)
+    //      products (A Bjj) A^T, then one atomic per thread and output. ----
 #pragma unroll
     for (int k = 0; k < kAccComps; ++k) sh[k * NT + tau] = active ? acc[k] : 0.0f;
+    cp_async_wait<0>();
     __syncthreads();
-    double Bl[21], vj[6];
-    if (tau < d) {
-#pragma unroll
-      for (int k = 0; k < 21; ++k) { double s = 0.0; for (int kp = 0; kp < Tp; ++kp) s += (double)sh[k * NT + kp * d + tau]; Bl[k] = s; }
-#pragma unroll
-      for (int k = 0; k < 6; ++k) { double s = 0.0; for (int kp = 0; kp < Tp; ++kp) s += (double)sh[(21 + k) * NT + kp * d + tau]; vj[k] = s; }
-    }
-    __syncthreads();
-    double *outD = reinterpret_cast<double *>(sh);          // [kFlushPos][kFlushOuts] doubles = 23 KB <= 27 KB
+    double *sumD = reinterpret_cast<double *>(spatch);          // [kFlushPos][27]  (patches / prefetch buffers are dead)
+    double *ABs = sumD + kFlushPos * kAccComps;                  // [kFlushPos][6][6]  A Bjj
+    double *outD = ABs + kFlushPos * 36;                         // [kFlushPos][90]
     for (int pb = 0; pb < d; pb += kFlushPos) {
-      if (tau >= pb && tau < min(pb + kFlushPos, d)) {       // tau < d: kappa == 0, so `pc` belongs to position tau
-        double *o = outD + (tau - pb) * kFlushOuts;
-        double AB[6][6];                                     // A * Bjj   (column c of Bjj is its row c)
+      const int np = min(kFlushPos, d - pb);
+      for (int x = tau; x < np * kAccComps; x += NT) {
+        const int pl = x / kAccComps, k = x - pl * kAccComps;
+        double sv = 0.0;
+        for (int kp = 0; kp < Tp; ++kp) sv += (double)sh[k * NT + kp * d + pb + pl];
+        sumD[x] = sv;
+      }
+      __syncthreads();
+      for (int x = tau; x < np * 7; x += NT) {                   // (position, column c of Bjj) and (position, vj)
+        const int pl = x / 7, c = x - pl * 7, pos = pb + pl;
+        float Rm[9];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          double col[6], out[6];
+        for (int k = 0; k < 9; ++k) Rm[k] = shc[k * NT + pos];
+        const Vec3 tt{shc[9 * NT + pos], shc[10 * NT + pos], shc[11 * NT + pos]};
+        const double *Sm = sumD + pl * kAccComps;
+        double *o = outD + pl * kFlushOuts;
+        double col[6], res[6];
+        if (c < 6) {
 #pragma unroll
-          for (int a = 0; a < 6; ++a) col[a] = a >= c ? Bl[tri(a, c)] : Bl[tri(c, a)];
-          adjT_apply_d(pc.R, pc.t, col, out);
+          for (int a = 0; a < 6; ++a) col[a] = Sm[a >= c ? tri(a, c) : tri(c, a)];   // column c of Bjj (= its row c)
+          adjT_apply_d(Rm, tt, col, res);
 #pragma unroll
-          for (int a = 0; a < 6; ++a) AB[a][c] = out[a];
-        }
-        double vi[6];
-        adjT_apply_d(pc.R, pc.t, vj, vi);
+          for (int a = 0; a < 6; ++a) { ABs[pl * 36 + a * 6 + c] = res[a]; o[42 + 6 * a + c] = -res[a]; }   // Bij = -A Bjj, ba.py:280
+        } else {
 #pragma unroll
-        for (int k = 0; k < 21; ++k) o[k] = Bl[k];                                    // Bjj, ba.py:282
+          for (int a = 0; a < 6; ++a) col[a] = Sm[21 + a];
+          adjT_apply_d(Rm, tt, col, res);
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-          double row[6];
-          adjT_apply_d(pc.R, pc.t, AB[a], row);                                       // Bii = (A Bjj) A^T, ba.py:279
+          for (int a = 0; a < 6; ++a) { o[78 + a] = col[a]; o[84 + a] = -res[a]; }   // vj ba.py:290; vi = -A vj ba.py:289
 #pragma unroll
-          for (int b = 0; b <= a; ++b) o[21 + tri(a, b)] = row[b];
-#pragma unroll
-          for (int b = 0; b < 6; ++b) o[42 + 6 * a + b] = -AB[a][b];                  // Bij = -A Bjj, ba.py:280
-          o[78 + a] = vj[a];                                                          // ba.py:290
-          o[84 + a] = -vi[a];                                                         // vi = -A vj, ba.py:289
+          for (int k = 0; k < 21; ++k) o[k] = Sm[k];                                  // Bjj, ba.py:282
         }
       }
       __syncthreads();
-      const int np = min(kFlushPos, d - pb);
+      for (int x = tau; x < np * 6; x += NT) {                   // (position, row a): Bii = (A Bjj) A^T, ba.py:279
+        const int pl = x / 6, a = x - pl * 6, pos = pb + pl;
+        float Rm[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rm[k] = shc[k * NT + pos];
+        const Vec3 tt{shc[9 * NT + pos], shc[10 * NT + pos], shc[11 * NT + pos]};
+        double rowv[6], res[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) rowv[c] = ABs[pl * 36 + a * 6 + c];
+        adjT_apply_d(Rm, tt, rowv, res);
+        double *o = outD + pl * kFlushOuts + 21;
+        for (int b2 = 0; b2 <= a; ++b2) o[tri(a, b2)] = res[b2];
+      }
+      __syncthreads();
       for (int x = tau; x < np * kFlushOuts; x += NT) {
         const int pl = x / kFlushOuts, o = x - pl * kFlushOuts;
         const int pi = pv.pat_i[pat0 + pb + pl], pj = pv.pat_j[pat0 + pb + pl];

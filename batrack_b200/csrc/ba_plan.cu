@@ -234,6 +234,17 @@ __global__ void k_group_slots(const int *__restrict__ g_t0, const int *__restric
 
 __global__ void k_zero_last(long long *p, int idx) { p[idx] = 0; }
 
+__global__ void k_chunk_desc(PlanView v, ChunkDesc *out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= v.n_chunks) return;
+  ChunkDesc d;
+  d.g = v.c_grp[c]; d.t0 = v.c_t0[c]; d.t1 = v.c_t0[c + 1]; d.gt0 = v.g_t0[d.g];
+  d.pat0 = v.g_pat[d.g]; d.d = v.g_pat[d.g + 1] - d.pat0; d.W = v.g_W[d.g]; d.ebase = v.tptr[d.gt0];
+  d.nm = v.g_nm[d.g]; d.R = v.ms_ptr[2 * d.pat0 + d.g + d.nm]; d.pad0 = d.pad1 = 0;
+  d.eoff = v.g_eoff[d.g]; d.pad2 = 0;
+  out[c] = d;
+}
+
 // ---- small RAII helpers (host) ---------------------------------------------------------------
 struct Scratch {
   cudaStream_t s;
@@ -446,6 +457,13 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     v.slot_pose = slot_pose; v.slot_ptr = slot_ptr; v.slot_items = slot_items;
     v.g_nm = g_nm; v.ms_ptr = ms_ptr; v.ms_slot = ms_slot; v.pat_ri = pat_ri; v.pat_rj = pat_rj; v.dmax = hmeta[META_DMAX];
     v.c_t0 = unit_t0[0]; v.c_grp = unit_grp[0]; v.u_t0 = unit_t0[1]; v.u_grp = unit_grp[1];
+
+    {
+      ChunkDesc *cd;
+      PL_CUDA(own(pl, &cd, v.n_chunks));
+      k_chunk_desc<<<cdiv(v.n_chunks, TB), TB, 0, s>>>(v, cd); PL_LAUNCH();
+      v.cdesc = cd;
+    }
 
     BaPlanInfo &in = pl->info;
     in.n_edges = E; in.n_poses = N; in.n_patches = NM; in.n_total = hmeta[META_MAXPOSE] + 1;

@@ -143,6 +143,40 @@ def cpu_baseline(prob, budget_s=25.0):
             "sample": f"{reps} full cfg3 BA calls after 1 warm-up, oracle/ba_oracle.py mode=dense fp32 ({dt:.2f} s/call)"}
 
 
+def davis_like_update(dev, reps=20):
+    """BASELINE.json configs[1] stand-in (DAVIS data and the tracker checkpoint are absent): the reference's own graph
+    bookkeeping replayed with configs/davis_demo.yaml parameters (400 patches/frame, S_slam 12, kf_stride 2,
+    OPTIMIZATION_WINDOW 15) on synthetic tracks; one BATRACK.update() = ITER(4) x {pose call, structure-only call}
+    (main/batrack.py:869-875). Reported: milliseconds per update(), device time, inputs resident."""
+    from batrack_b200 import synth
+    from batrack_b200.ba import BA_rgbd_droid
+    from batrack_b200.lietorch import SE3
+    ps, w_all = synth.make_slam_problem(n_frames=25, patches_per_frame=400, seed=7, buffer_size=64)
+    t = {k: v.to(dev) for k, v in ps.as_torch().items()}
+    w_pose, w_full = t["weights"], torch.from_numpy(w_all).to(dev)[None]
+
+    def update():
+        G, p = SE3(t["poses"]), t["patches"]
+        for _ in range(4):
+            for w, so in ((w_pose, False), (w_full, True)):
+                G, p = BA_rgbd_droid(G, p, t["patches_monodisp"], t["intrinsics"], t["targets_2d"], None, w, ps.lmbda,
+                                     t["ii"], t["jj"], t["kk"], ps.bounds, ep=ps.ep, fixedp=ps.fixedp, structure_only=so,
+                                     loss=ps.loss, alpha=ps.alpha)
+        return G, p
+
+    for _ in range(3):
+        update()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        update()
+    e1.record()
+    torch.cuda.synchronize()
+    return {"edges": ps.E, "free_poses": int(max(ps.ii.max(), ps.jj.max())) + 1 - ps.fixedp, "ba_calls_per_update": 8,
+            "ms_per_update": e0.elapsed_time(e1) / reps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,6 +380,8 @@ def main():
                      "traffic": traffic, "algorithmic_bytes": alg_rank, "kernel_ms": edge_ms, "peak_source": peak_src},
         "kernels": {k: {"ms": v, "share": v / tot} for k, v in stages.items()},
     }
+    if world == 1:
+        out["other_workloads"] = {"davis_like_window": davis_like_update(dev)}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(prob)
     print(json.dumps(out))
