@@ -106,7 +106,8 @@ int set_cuda_error(cudaError_t e, const char *what);
 void layout_for(const BaPlan *p, int fixedp, int *n, int *bw, int *ld, int *off, int64_t *s_floats);
 constexpr int kMmaMaxBw = 120;        // widest band the 16x16-tile register window of the DMMA solver covers
 size_t solve_mma_smem_bytes(int M);
-int launch_solve_band_mma(const CallView &cv, int allow_retry, double *Wg, cudaStream_t s);
+size_t solve_mma_scratch_doubles(int M, int bw);
+int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, cudaStream_t s);
 }  // namespace ba
 
 #define BA_CUDA(call)                                                         \

@@ -310,7 +310,7 @@ static int alloc_workspace(BaPlan *pl) {
     BA_CUDA(own(pl, &pl->SY, need));
     BA_CUDA(own(pl, &pl->L, sf + 8));
     BA_CUDA(own(pl, &pl->dX, 6 * (size_t)n + 8));
-    BA_CUDA(own(pl, &pl->Wg, 8 * (6 * (size_t)n + 8)));
+    BA_CUDA(own(pl, &pl->Wg, solve_mma_scratch_doubles(6 * n, std::min(bw, kMmaMaxBw)) + 64));   // solver scratch
     pl->sy_floats = need;
   }
   pl->info.banded = (ld != 6 * n) ? 1 : 0;

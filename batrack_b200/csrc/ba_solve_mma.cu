@@ -86,7 +86,20 @@ __device__ __forceinline__ long long clk_after(double dep) { long long t; asm vo
 __device__ __forceinline__ long long clk_after(int dep) { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep)); return t; }
 #define BA_TRD(slot, dep) do { if (trace && lane == 0) trace[(size_t)J * 16 + (slot)] = clk_after(dep); } while (0)
 
-__global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, int allow_retry, double *__restrict__ Wg,
+// cluster-wide barrier (both CTAs of the twisted factorisation); release/acquire orders global memory
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// twist != 0: launched as a cluster of two CTAs. CTA 0 eliminates tile columns [0, Jm0) of the matrix, CTA 1
+// the last Jm1 tile columns, working on the index-reversed matrix (same code, reversed coordinates); CTA 1
+// then hands CTA 0 what its eliminations contributed to the 16 middle tile columns, CTA 0 finishes the
+// middle, solves it, and both back-substitute their side in parallel ("burn at both ends": the serial chain
+// of a banded Cholesky is halved). Exchange through global scratch XD + cluster barriers.
+__global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, int allow_retry, double *__restrict__ Wg_all,
+                                                                   double *__restrict__ L_all, double *__restrict__ XD,
+                                                                   int *__restrict__ gfl, int twist,
                                                                    long long *__restrict__ trace) {
   extern __shared__ double dsm[];
   const int tau = threadIdx.x, lane = tau & 31, hw = tau >> 5;
@@ -95,6 +108,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
   const int g = lane >> 2, q = lane & 3;
   const int M = cv.M, bw = cv.bw, ld = cv.ld, off = cv.off;
   const int NT8 = (M + 7) >> 3, Mp = NT8 * 8;
+  const int side = twist ? (int)blockIdx.x : 0;
+  const int Jm0 = (NT8 - 16) / 2, Jm1 = NT8 - 16 - Jm0;             // columns eliminated from the top / from the bottom
+  const int c1 = twist ? (side ? Jm1 : Jm0) : NT8;                  // end of this side's first segment
+  const int NTloc = twist ? c1 + 16 : NT8;                          // tiles this side ever sees (local coordinates)
+  const int nseg = (twist && side == 0) ? 2 : 1;
+  double *__restrict__ Wg = Wg_all + (size_t)side * NT8 * 64;
+  double *__restrict__ L = L_all + (size_t)side * Mp * (bw + 1);    // this side's factor, local band storage
+  auto Lg = [&](int rl, int cl) { return (size_t)rl * bw + cl + bw; };
   double *z = dsm;                         // [Mp]   right-hand side -> forward solution -> solution
   double *Psm = z + Mp;                    // [17][8][kPs]  panel tiles L_aJ by circular position; tile 16 = zeros
   double *Nsm = Psm + 17 * kTs;            // [17][8][kPs]  the same, negated (A operand of C -= L L^T)
@@ -108,9 +129,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
   unsigned *tabX = tabP + 16 * 8;          // [16][8] the other position of those two tiles, 8 bits each
   double *Esm = reinterpret_cast<double *>(tabX + 16 * 8);         // [8 warps][2 slots][64] next column's e-tiles
   double *xsol = dd;                                               // solution of the back substitution (dd is dead then)
-  __shared__ int s_fail, s_nan;
+  __shared__ int s_fail, s_nan, s_abort;
   const double *__restrict__ S = cv.S;
-  double *__restrict__ L = cv.L;
   const double ep = (double)cv.ep;
   auto Sg = [&](int r, int c) { return (size_t)r * ld + c + off; };
   int status = 0;
@@ -156,9 +176,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
     // value of S at (r, c), r >= c, with identity padding beyond M. The damping of the diagonal
     // (ba.py:67) is added from `dd` when the diagonal tile is factored, so that nothing here consumes the
     // loaded value and the global latency of a refill hides behind the rest of the step.
-    auto Aval = [&](int r, int c) -> double {
+    auto Aval = [&](int rl, int cl) -> double {                  // local coordinates (reversed on side 1)
+      if (cl > rl) return 0.0;
+      const int r = side ? Mp - 1 - cl : rl, c = side ? Mp - 1 - rl : cl;   // global, r >= c
       if (r >= M) return r == c ? 1.0 : 0.0;
-      if (c > r || r - c > bw) return 0.0;
+      if (r - c > bw) return 0.0;
       return S[Sg(r, c)];
     };
     auto load_tile = [&](int a, int b, double &c0, double &c1) {   // tile (a, b), a >= b, C-fragment layout
@@ -167,16 +189,26 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
       c1 = Aval(r, c + 1);
     };
 
-    for (int r = tau; r < Mp; r += kMmaThreads) {
-      z[r] = r < M ? cv.y[r] : 0.0;
-      dd[r] = r < M ? ep + lm * S[Sg(r, r)] : 0.0;                 // A = S + (ep + lm * S) .* I, ba.py:67
+    for (int rl = tau; rl < Mp; rl += kMmaThreads) {
+      const int r = side ? Mp - 1 - rl : rl;
+      z[rl] = r < M ? cv.y[r] : 0.0;
+      dd[rl] = r < M ? ep + lm * S[Sg(r, r)] : 0.0;                // A = S + (ep + lm * S) .* I, ba.py:67
     }
-    if (tau == 0) { s_fail = 0; s_nan = 0; }
+    if (tau == 0) { s_fail = 0; s_nan = 0; s_abort = 0; }
+    int *gf = gfl + 4 * attempt;                                   // [0] side 0 failed, [1] side 1 failed, [2] NaN
     __syncthreads();                                               // z, dd, tables, zero tiles visible
     bool failed = false;
+    const int nsegs = twist ? 2 : 1;
     if (is_factor) {
       // =================== factor warp: [A] for column J while the tile warps still update column J-1 ==========
-      for (int J = 0; J < NT8; ++J) {
+      for (int seg = 0; seg < nsegs; ++seg) {
+      if (seg == 1) {                                              // twist hand-over (see the tile-warp branch)
+        __syncthreads();
+        cluster_sync();
+        __syncthreads();
+      }
+      const int jb = seg ? c1 : 0, je = seg ? ((side == 0 && !s_abort) ? NTloc : c1) : c1;
+      for (int J = jb; J < je; ++J) {
         BA_TR(8);
         bar_sync(2, 64);                                           // tile (J,J) (+ damping) is in Dsm, z_J is final
         // every lane factors the 8x8 block redundantly in registers (no divergence, no extra exchange)
@@ -231,6 +263,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
         bar_arrive(3, 32 * (kMmaWarps + 1));                       // W_J, zJ (or the failure flag) published
         if (!ok) { failed = true; break; }
       }
+      }
     } else if (is_tile) {
       // =================== tile warps ===========================================================================
       double ct[kTilesPerWarp][2];
@@ -238,7 +271,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
       for (int t = 0; t < kTilesPerWarp; ++t) {
         const int x = c_px[t * 8 + warp], y = c_py[t * 8 + warp];   // x <= y: initial window holds tile (y, x)
         ct[t][0] = ct[t][1] = 0.0;
-        if (y < NT8) load_tile(y, x, ct[t][0], ct[t][1]);
+        if (y < NTloc) load_tile(y, x, ct[t][0], ct[t][1]);
       }
       double *myE = Esm + warp * 128 + 2 * lane;                    // this warp's two e-tile slots (fragment layout)
       {                                                             // e-tiles of column 0 = "next" tiles of position 15
@@ -260,7 +293,63 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
       // the warp's shared slots (written by the previous [U]) into fixed registers, so the unrolled code never
       // indexes the tile registers dynamically. Their refills are loaded into fixed registers at the top of the
       // step and moved into the tile registers by predicated moves inside the [U] loop.
-      for (int J = 0; J < NT8; ++J) {
+      for (int seg = 0; seg < nsegs; ++seg) {
+      if (seg == 1) {
+        // ---- twist hand-over. Side 1: what its eliminations did to the 16 middle tile columns (window minus
+        //      the untouched matrix) and to the right-hand side goes to XD in its local coordinates. Side 0 adds
+        //      it to its window, refreshes the e-tile slots and publishes the diagonal tile of column c1. ----
+        __syncthreads();
+        const int ec = c1 & 15;
+        if (side == 1 && !s_fail) {
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) {
+            const int x = c_px[t * 8 + warp], y = c_py[t * 8 + warp];
+            const int ax = c1 + ((x - ec) & 15), ay = c1 + ((y - ec) & 15);
+            const int rl = 8 * max(ax, ay) + g, cl = 8 * min(ax, ay) + 2 * q;
+            double *d = XD + (size_t)(rl - 8 * c1) * 128 + (cl - 8 * c1);
+            d[0] = ct[t][0] - Aval(rl, cl);
+            d[1] = ct[t][1] - Aval(rl, cl + 1);
+          }
+          const int i = warp * 32 + lane;
+          if (i < 128) { const int r = Mp - 1 - (8 * c1 + i); XD[16384 + i] = z[8 * c1 + i] - (r < M ? cv.y[r] : 0.0); }
+        }
+        if (tau == 0) gf[side] = s_fail;
+        cluster_sync();
+        if (tau == 0) s_abort = side == 0 ? (gf[1] | s_fail) : s_fail;
+        __syncthreads();
+        if (side == 0 && !s_abort) {
+#pragma unroll
+          for (int t = 0; t < kTilesPerWarp; ++t) {
+            const int x = c_px[t * 8 + warp], y = c_py[t * 8 + warp];
+            const int ax = c1 + ((x - ec) & 15), ay = c1 + ((y - ec) & 15);
+            const int r = 8 * max(ax, ay) + g, c = 8 * min(ax, ay) + 2 * q;
+            const double *d = XD + (size_t)(Mp - 1 - c - 8 * Jm1) * 128 + (Mp - 1 - r - 8 * Jm1);
+            ct[t][0] += d[0];
+            ct[t][1] += d[-128];
+          }
+          const int i = warp * 32 + lane;
+          if (i < 128) z[8 * c1 + i] += XD[16384 + 127 - i];
+          {
+            const unsigned *tu = tabU + ((ec - 1) & 15) * 136 + warp;
+#pragma unroll
+            for (int t = 0; t < kTilesPerWarp; ++t) {
+              const unsigned o = tu[t * 8];
+              if (o & (4u << 24)) { double *d = myE + ((o >> 27) & 1u) * 64; d[0] = ct[t][0]; d[1] = ct[t][1]; }
+            }
+          }
+          bar_sync(1, 32 * kMmaWarps);                             // z of the middle complete before the factor warp reads it
+          if (warp == (ec & 7)) {
+            const double dmp = dd[8 * c1 + g];
+            const double d0 = (ec >> 3) ? ct[1][0] : ct[0][0], d1 = (ec >> 3) ? ct[1][1] : ct[0][1];
+            Dsm[g * kPs + 2 * q] = d0 + (2 * q == g ? dmp : 0.0);
+            Dsm[g * kPs + 2 * q + 1] = d1 + (2 * q + 1 == g ? dmp : 0.0);
+            bar_arrive(2, 64);
+          }
+          __syncwarp();
+        }
+      }
+      const int jb = seg ? c1 : 0, je = seg ? ((side == 0 && !s_abort) ? NTloc : c1) : c1;
+      for (int J = jb; J < je; ++J) {
         const int e = J & 15;
         const unsigned xo2 = tabX[e * 8 + warp];
         const int xo0 = xo2 & 0xff, xo1 = (xo2 >> 8) & 0xff;
@@ -275,7 +364,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
           for (int k = 0; k < 2; ++k) {
             ag[k] = J + ((xo[k] - e) & 15);                        // global tile row held at the other position
             rf[k][0] = rf[k][1] = 0.0;                             // position e next stands for tile index J + 16
-            if (an < NT8) load_tile(an, xo[k] == e ? an : ag[k], rf[k][0], rf[k][1]);
+            if (an < NTloc) load_tile(an, xo[k] == e ? an : ag[k], rf[k][0], rf[k][1]);
           }
         }
         if (warp == 0) BA_TR(1);
@@ -315,9 +404,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
             if (xo[k] != e) {
               Psm[xo[k] * kTs + lo] = p[k][0]; Psm[xo[k] * kTs + lo + 1] = p[k][1];
               Nsm[xo[k] * kTs + lo] = -p[k][0]; Nsm[xo[k] * kTs + lo + 1] = -p[k][1];
-              if (q == 0 && r < Mp) z[r] -= part[k];
-              if (r < M) {                                         // columns of tile J are < M whenever a row below is
-                double *lp = L + Sg(r, cJ);
+              if (r < 8 * NTloc) {                                 // tiles below this side's matrix are all zero
+                if (q == 0) z[r] -= part[k];
+                double *lp = L + Lg(r, cJ);
                 if (r - cJ <= bw) lp[0] = p[k][0];
                 if (r - cJ - 1 <= bw) lp[1] = p[k][1];
               }
@@ -331,7 +420,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
         const unsigned *tu = tabU + e * 136 + warp;
         const double *An = Nsm + g * kPs + q, *Bp = Psm + g * kPs + q;
         const int en = (J + 1) & 15;
-        const bool have_next = J + 1 < NT8;
+        const bool have_next = J + 1 < je;
         const bool own_next = have_next && warp == (en & 7);
         const bool is_prod = have_next && (xo0 == en || xo1 == en);
         const int tn = en >> 3;                                    // pair {en,en} is tile en/8 of tile warp en%8
@@ -384,80 +473,127 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
         if (warp == 0) BA_TR(5);
         __syncwarp();                                              // slots written by this warp, read by it next step
       }
+      }
     }
     __syncthreads();
-    if (failed) {                                                   // dX = 0 (ba.py:12-13); no NaN -> no retry
-      for (int r = tau; r < M; r += kMmaThreads) cv.dX[r] = 0.0;
-      status |= (attempt == 0) ? 1 : 4;
-      break;
-    }
+    (void)failed;
+    const bool bad = s_fail || s_abort;                             // this side could not factor (or was told to stop)
+    const int ncols = (twist && side == 1) ? c1 : NTloc;            // tile columns of L (and W_J) this side owns
 
-    // ---- backward substitution L^T x = z by tile rows, descending. Stage s holds rows 8J..8J+7 of L
-    //      restricted to columns [8(J-15), 8J) plus W_J. ----
+    // ---- backward substitution L^T x = z by tile rows, descending, in local coordinates. Stage s holds rows
+    //      8J..8J+7 of L restricted to columns [8(J-15), 8J) plus W_J. On side 1 the middle rows J >= c1 were not
+    //      factored here: their solution is given (x_mid from side 0) and only their coupling to the columns this
+    //      side owns (which it did compute) is applied. ----
     auto stage_load = [&](int J, int sidx) {
       double *dst = Lst + (size_t)sidx * (8 * 128 + 64);
       for (int o = tau; o < 8 * 120 + 64; o += kMmaThreads) {
         if (o < 8 * 120) {
           const int gg = o / 120, xcol = o - gg * 120;
           const int r = 8 * J + gg, c = 8 * (J - 15) + xcol;
-          if (r < M && c >= 0 && r - c <= bw) cp_async8_d(dst + gg * 128 + xcol, L + Sg(r, c));
+          if (c >= 0 && c < 8 * ncols && r - c <= bw) cp_async8_d(dst + gg * 128 + xcol, L + Lg(r, c));
           else dst[gg * 128 + xcol] = 0.0;
-        } else {
+        } else if (J < ncols) {
           cp_async8_d(dst + 8 * 128 + (o - 8 * 120), Wg + (size_t)J * 64 + (o - 8 * 120));
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     __threadfence_block();
-    // kBackStages - 1 stages in flight: one (possibly empty) cp.async group per tile row
-    for (int k = 0; k < kBackStages - 1; ++k) {
-      if (NT8 - 1 - k >= 0) stage_load(NT8 - 1 - k, (NT8 - 1 - k) % kBackStages);
-      else asm volatile("cp.async.commit_group;" ::: "memory");
+    bool anybad = bad;
+    if (twist && side == 1) {                                      // wait for x_mid
+      cluster_sync();
+      anybad = bad || gf[0] != 0 || gf[1] != 0;
+      if (!anybad) {
+        for (int i = tau; i < 128; i += kMmaThreads) xsol[8 * c1 + i] = XD[16384 + 128 + (Mp - 1 - (8 * c1 + i) - 8 * Jm0)];
+      }
+      __syncthreads();
     }
-    for (int J = NT8 - 1; J >= 0; --J) {
-      asm volatile("cp.async.wait_group %0;" ::"n"(kBackStages - 2) : "memory");
-      __syncthreads();                                             // stage J landed; iteration J+1 fully retired
-      if (J - (kBackStages - 1) >= 0) stage_load(J - (kBackStages - 1), (J - (kBackStages - 1)) % kBackStages);
-      else asm volatile("cp.async.commit_group;" ::: "memory");
-      const double *st = Lst + (size_t)(J % kBackStages) * (8 * 128 + 64);
-      const double *Wj = st + 8 * 128;                             // W_J row-major 8x8
-      // x_J = W_J^T z_J, computed redundantly by every thread that uses it (broadcast loads, no exchange, one
-      // barrier per tile row); the solution goes to xsol so that z_J stays readable during the iteration.
-      if (tau < 32 + 120) {
-        double zz[8], xJ[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) zz[k] = z[8 * J + k];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int k = i; k < 8; k += 2) { s0 += Wj[k * 8 + i] * zz[k]; if (k + 1 < 8) s1 += Wj[(k + 1) * 8 + i] * zz[k + 1]; }
-          xJ[i] = s0 + s1;
+    bool synced2 = !(twist && side == 0);                          // side 0 owes the cluster one barrier (x_mid hand-over)
+    if (!anybad) {
+      // kBackStages - 1 stages in flight: one (possibly empty) cp.async group per tile row
+      for (int k = 0; k < kBackStages - 1; ++k) {
+        if (NTloc - 1 - k >= 0) stage_load(NTloc - 1 - k, (NTloc - 1 - k) % kBackStages);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      for (int J = NTloc - 1; J >= 0; --J) {
+        if (!synced2 && J == c1 - 1) {                             // middle solved: publish it, then carry on downwards
+          __syncthreads();
+          for (int i = tau; i < 128; i += kMmaThreads) XD[16384 + 128 + i] = xsol[8 * c1 + i];
+          if (tau == 0) gf[0] = 0;
+          cluster_sync();
+          synced2 = true;
+          if (gf[1] != 0) { anybad = true; break; }
         }
-        if (tau == 0) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kBackStages - 2) : "memory");
+        __syncthreads();                                           // stage J landed; iteration J+1 fully retired
+        if (J - (kBackStages - 1) >= 0) stage_load(J - (kBackStages - 1), (J - (kBackStages - 1)) % kBackStages);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        const double *st = Lst + (size_t)(J % kBackStages) * (8 * 128 + 64);
+        const double *Wj = st + 8 * 128;                           // W_J row-major 8x8
+        // x_J = W_J^T z_J, computed redundantly by every thread that uses it (broadcast loads, no exchange, one
+        // barrier per tile row); the solution goes to xsol so that z_J stays readable during the iteration.
+        if (tau < 32 + 120) {
+          double xJ[8];
+          if (J < ncols) {
+            double zz[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) xsol[8 * J + i] = xJ[i];
-        }
-        if (tau >= 32) {
-          const int xcol = tau - 32, c = 8 * (J - 15) + xcol;
-          if (c >= 0) {
-            double s0 = 0.0, s1 = 0.0;
+            for (int k = 0; k < 8; ++k) zz[k] = z[8 * J + k];
 #pragma unroll
-            for (int gg = 0; gg < 8; gg += 2) { s0 += st[gg * 128 + xcol] * xJ[gg]; s1 += st[(gg + 1) * 128 + xcol] * xJ[gg + 1]; }
-            z[c] -= s0 + s1;
+            for (int i = 0; i < 8; ++i) {
+              double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+              for (int k = i; k < 8; k += 2) { s0 += Wj[k * 8 + i] * zz[k]; if (k + 1 < 8) s1 += Wj[(k + 1) * 8 + i] * zz[k + 1]; }
+              xJ[i] = s0 + s1;
+            }
+            if (tau == 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) xsol[8 * J + i] = xJ[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xJ[i] = xsol[8 * J + i];   // given (side 1, middle rows)
+          }
+          if (tau >= 32) {
+            const int xcol = tau - 32, c = 8 * (J - 15) + xcol;
+            if (c >= 0) {
+              double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+              for (int gg = 0; gg < 8; gg += 2) { s0 += st[gg * 128 + xcol] * xJ[gg]; s1 += st[(gg + 1) * 128 + xcol] * xJ[gg + 1]; }
+              z[c] -= s0 + s1;
+            }
           }
         }
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    if (!synced2) {                                                // failed before the hand-over: still meet the barrier
+      if (tau == 0) gf[0] = 1;
+      cluster_sync();
+      synced2 = true;
+      anybad = true;
     }
     __syncthreads();
+    // ---- write this side's rows of dX (zeros if any factorisation failed, ba.py:12-13), NaN check ----
+    const int nrows = 8 * ((twist && side == 1) ? c1 : NTloc);
     int nan_local = 0;
-    for (int r = tau; r < M; r += kMmaThreads) { const double v = xsol[r]; cv.dX[r] = v; nan_local |= (v != v); }
+    for (int rl = tau; rl < nrows; rl += kMmaThreads) {
+      const int r = side ? Mp - 1 - rl : rl;
+      if (r < M) { const double v = anybad ? 0.0 : xsol[rl]; cv.dX[r] = v; nan_local |= (v != v); }
+    }
     if (nan_local) s_nan = 1;
     __syncthreads();
-    if (s_nan && allow_retry && attempt == 0) { status |= 2; __syncthreads(); continue; }   // ba.py:324-325
+    int any_nan = s_nan;
+    if (twist) {
+      if (tau == 0 && s_nan) atomicOr(&gf[2], 1);
+      cluster_sync();
+      any_nan = gf[2];
+      anybad = anybad || gf[0] != 0 || gf[1] != 0;
+    }
+    if (anybad) { status |= (attempt == 0) ? 1 : 4; break; }         // no NaN possible -> no retry
+    if (any_nan && allow_retry && attempt == 0) { status |= 2; __syncthreads(); continue; }   // ba.py:324-325
     break;
   }
-  if (tau == 0) cv.status[0] = status;
+  if (tau == 0 && side == 0) cv.status[0] = status;
 }
 
 size_t solve_mma_smem_bytes(int M) {
@@ -466,20 +602,46 @@ size_t solve_mma_smem_bytes(int M) {
          (16 * 136 + 2 * 16 * 8) * sizeof(unsigned);
 }
 
-int launch_solve_band_mma(const CallView &cv, int allow_retry, double *Wg, cudaStream_t s) {
+// doubles of scratch the solver needs besides [S | y]: both sides' L (local band storage) and W tiles, the
+// hand-over block, and a few ints of flags
+size_t solve_mma_scratch_doubles(int M, int bw) {
+  const size_t Mp = ((size_t)(M + 7) / 8) * 8;
+  return 2 * Mp * (bw + 1) + 2 * (Mp / 8) * 64 + (128 * 128 + 256) + 8;
+}
+
+int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, cudaStream_t s) {
   static bool attr_set = false;
   static long long *trace = nullptr;
   static int trace_left = 0;
+  static int twist_min = 64;
   if (!attr_set) {
     BA_CUDA(cudaFuncSetAttribute(k_solve_band_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
     if (const char *e = getenv("BA_TRACE")) { trace_left = atoi(e); BA_CUDA(cudaMalloc(&trace, 16 * 8 * 4096)); }
+    if (const char *e = getenv("BA_TWIST_MIN")) twist_min = atoi(e);        // tile columns from which two CTAs are used
     attr_set = true;
   }
-  const bool tr = trace && trace_left > 0 && (cv.M + 7) / 8 <= 4096;
-  k_solve_band_mma<<<1, kMmaThreads, solve_mma_smem_bytes(cv.M), s>>>(cv, allow_retry, Wg, tr ? trace : nullptr);
+  const size_t Mp = ((size_t)(cv.M + 7) / 8) * 8;
+  const int nt = (int)(Mp / 8);
+  double *L_all = scratch, *W_all = L_all + 2 * Mp * (cv.bw + 1), *XD = W_all + 2 * (Mp / 8) * 64;
+  int *gfl = reinterpret_cast<int *>(XD + 128 * 128 + 256);
+  const int twist = nt >= twist_min ? 1 : 0;
+  const bool tr = trace && trace_left > 0 && nt <= 4096 && !twist;
+  BA_CUDA(cudaMemsetAsync(gfl, 0, 8 * sizeof(int), s));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(twist ? 2 : 1);
+  cfg.blockDim = dim3(kMmaThreads);
+  cfg.dynamicSmemBytes = solve_mma_smem_bytes(cv.M);
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = twist ? 2 : 1;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  BA_CUDA(cudaLaunchKernelEx(&cfg, k_solve_band_mma, cv, allow_retry, W_all, L_all, XD, gfl, twist, tr ? trace : (long long *)nullptr));
   BA_LAUNCH_CHECK();
   if (tr && --trace_left == 0) {       // debug only: synchronises and prints mean phase lengths in SM cycles
-    const int nt = (cv.M + 7) / 8;
     std::vector<long long> h((size_t)nt * 16);
     BA_CUDA(cudaStreamSynchronize(s));
     BA_CUDA(cudaMemcpy(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost));
