@@ -52,7 +52,7 @@ constexpr int kPosFloats = 20;    // per-position constants: R[9] t[3] 1/fxi 1/f
 constexpr int kFlushPos = 24;     // positions flushed per round (27+36+90 doubles each in the dead prefetch buffers)
 constexpr int kFlushOuts = 90;    // Bjj[21] Bii[21] Bij[36] vj[6] vi[6]
 constexpr int kStagePasses = 4;   // passes whose targets / weights are prefetched together (2 stages in flight)
-constexpr size_t kEdgeSmemBytes = (size_t)(kAccComps + kPosFloats + 3) * kEdgeThreads * sizeof(float) +
+constexpr size_t kEdgeSmemBytes = (size_t)(kAccComps + kPosFloats + 4) * kEdgeThreads * sizeof(float) +
                                   (size_t)2 * kStagePasses * 2 * kEdgeThreads * sizeof(float2);
 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
   extern __shared__ __align__(16) float dyn_smem[];
   float *sh = dyn_smem;                                 // [27 NT] staging during passes; accumulators / outputs at flush
   float *shc = sh + kAccComps * NT;                     // [20 NT] per-position constants
-  float *spatch = shc + kPosFloats * NT;                // [3 NT]  (x, y, inverse depth) of the chunk's tracks
-  float2 *sin = reinterpret_cast<float2 *>(spatch + 3 * NT);   // [2 stages][kStagePasses][2][NT] target / weight
+  float *spatch = shc + kPosFloats * NT;                // [4 NT]  (x, y, inverse depth, mono disparity) of the chunk's tracks
+  float2 *sin = reinterpret_cast<float2 *>(spatch + 4 * NT);   // [2 stages][kStagePasses][2][NT] target / weight
   const int tau = threadIdx.x;
   const ChunkDesc cd = pv.cdesc[blockIdx.x];
   const int g = cd.g, pat0 = cd.pat0, d = cd.d;
@@ -98,8 +98,10 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
 
   // ---- the chunk's patches (gathered through kx once), and per-position constants, once per CTA ----
   for (int x = tau; x < t1 - t0; x += NT) {
-    const float *pp = cv.patches + 3 * (size_t)__ldg(pv.kx + t0 + x);
+    const size_t kp = (size_t)__ldg(pv.kx + t0 + x);
+    const float *pp = cv.patches + 3 * kp;
     spatch[x] = __ldg(pp); spatch[NT + x] = __ldg(pp + 1); spatch[2 * NT + x] = __ldg(pp + 2);
+    spatch[3 * NT + x] = cv.monodisp ? __ldg(cv.monodisp + kp) : 0.0f;
   }
   if (tau < d) {
     const int i = pv.pat_i[pat0 + tau], j = pv.pat_j[pat0 + tau];
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
   float acc[kAccComps];
 #pragma unroll
   for (int k = 0; k < kAccComps; ++k) acc[k] = 0.0f;
-  const int outs_per_track = STRUCT_ONLY ? 2 : 6 * nm + 2;
+  const int outs_per_track = STRUCT_ONLY ? 1 : 6 * nm + 1;
 
   // ---- targets / weights: each thread prefetches its own edges, kStagePasses passes per cp.async group,
   //      two groups in flight; the loads of a whole stage overlap instead of one round trip per pass ----
@@ -226,11 +228,22 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
         }
         Erows[(size_t)(t - gt0) * rowlen + 6 * s + comp] = sum;
       } else {
-        const int comp = STRUCT_ONLY ? r : r - 6 * nm;                    // 0: C, 1: w
-        const float *src = stC + comp * NT + k2 * d;
-        float sum = 0.0f;
-        for (int x = 0; x < d; ++x) sum += src[x];
-        reinterpret_cast<float *>(cv.Cw + t)[comp] = sum;
+        // C and w of the track (ba.py:287,292), then the damped inverse Q and the prior-adjusted w
+        // (ba.py:296-311; BA: :184) — fused here so that no separate per-track kernel is needed
+        const float *src = stC + k2 * d;
+        float C = 0.0f, w = 0.0f;
+        for (int x = 0; x < d; ++x) { C += src[x]; w += src[NT + x]; }
+        const float lam = cv.lmbda_vec ? cv.lmbda_vec[t] : cv.lmbda;
+        if (cv.monodisp) {
+          const float md = spatch[3 * NT + (t - t0)];
+          const float mk = md > 1e-2f ? 1.0f : 0.0f;
+          C = C + mk * cv.alpha;
+          C = C + lam;
+          w = w - mk * cv.alpha * (spatch[2 * NT + (t - t0)] - md);
+        } else {
+          C = C + lam;
+        }
+        cv.Qw[t] = make_float2(1.0f / C, w);
       }
     }
     __syncthreads();
@@ -408,6 +421,8 @@ __global__ void k_edge_pass_long(PlanView pv, CallView cv) {
 __global__ void k_track_q(PlanView pv, CallView cv) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= pv.m) return;
+  const int g = pv.t_grp[t];
+  if (pv.g_pat[g + 1] - pv.g_pat[g] <= kEdgeThreads) return;     // the edge pass already wrote (Q, w) for this track
   const float2 cw = cv.Cw[t];
   const float lam = cv.lmbda_vec ? cv.lmbda_vec[t] : cv.lmbda;
   float C = cw.x, w = cw.y;
@@ -782,7 +797,27 @@ __global__ void k_patches_copy_clamp(const float *__restrict__ in, float *__rest
   out[3 * (size_t)k + 2] = fminf(fmaxf(in[3 * (size_t)k + 2], 1e-3f), 10.0f);   // clamp hits every patch, ba.py:333
 }
 
-__global__ void k_backsub(PlanView pv, CallView cv, int use_dx) {
+__device__ __forceinline__ void pose_retr_one(const CallView &cv, int i) {
+  float a[6] = {0, 0, 0, 0, 0, 0};
+  if (pose_free(i, cv)) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) a[c] = (float)cv.dX[6 * (i - cv.fixedp) + c];
+  }
+  Pose dXp = pose_exp(a);
+  float tmp[7];
+  pose_store(dXp, tmp);
+  Pose r = pose_mul(pose_load(tmp), pose_load(cv.poses + 7 * (size_t)i));   // mul re-loads both operands
+  pose_store(r, cv.poses_out + 7 * (size_t)i);
+}
+
+// blocks [0, nb_back): one warp per track; blocks beyond: pose retraction T <- Exp(dx) T for every pose of the
+// buffer, dx = 0 outside the window (ba.py:47-49,336-337; lietorch/groups.py:153-156), when retr_n > 0
+__global__ void k_backsub(PlanView pv, CallView cv, int use_dx, int nb_back, int retr_n) {
+  if ((int)blockIdx.x >= nb_back) {
+    const int i = ((int)blockIdx.x - nb_back) * blockDim.x + threadIdx.x;
+    if (i < retr_n) pose_retr_one(cv, i);
+    return;
+  }
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (t >= pv.m) return;
@@ -806,23 +841,6 @@ __global__ void k_backsub(PlanView pv, CallView cv, int use_dx) {
     const size_t k = (size_t)pv.kx[t];
     cv.patches_out[3 * k + 2] = fminf(fmaxf(cv.patches[3 * k + 2] + dz, 1e-3f), 10.0f);
   }
-}
-
-// pose retraction T <- Exp(dx) T for every pose of the buffer, dx = 0 outside the window
-// (ba.py:47-49,336-337; lietorch/groups.py:153-156)
-__global__ void k_pose_retr(CallView cv, int N) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  float a[6] = {0, 0, 0, 0, 0, 0};
-  if (pose_free(i, cv)) {
-#pragma unroll
-    for (int c = 0; c < 6; ++c) a[c] = (float)cv.dX[6 * (i - cv.fixedp) + c];
-  }
-  Pose dXp = pose_exp(a);
-  float tmp[7];
-  pose_store(dXp, tmp);
-  Pose r = pose_mul(pose_load(tmp), pose_load(cv.poses + 7 * (size_t)i));   // mul re-loads both operands
-  pose_store(r, cv.poses_out + 7 * (size_t)i);
 }
 
 // ---- debug: expand the lower (band) storage to a dense symmetric matrix, cast fp64 -> fp32 --------
@@ -895,7 +913,9 @@ extern "C" int ba_assemble(BaPlan *pl, const BaProblem *pb, void *stream_) {
     if (has_long) { k_edge_pass_long<false><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
   }
   BA_MARK(pl, BA_STAGE_TRACKQ, s);
-  k_track_q<<<(pv.m + 255) / 256, 256, 0, s>>>(pv, cv); BA_LAUNCH_CHECK();
+  if (has_long) {                    // the atomics path leaves raw (C, w) sums; everything else writes (Q, w) directly
+    k_track_q<<<(pv.m + 255) / 256, 256, 0, s>>>(pv, cv); BA_LAUNCH_CHECK();
+  }
   BA_MARK(pl, BA_STAGE_SCHUR, s);
   if (!so) {
     const int rowmax = 6 * pl->info.max_slots;
@@ -957,13 +977,12 @@ extern "C" int ba_solve_update(BaPlan *pl, const BaProblem *pb, void *stream_) {
   }
   BA_MARK(pl, BA_STAGE_BACKSUB, s);
   k_patches_copy_clamp<<<(pv.NM + 255) / 256, 256, 0, s>>>(pb->patches, pb->patches_out, pv.NM); BA_LAUNCH_CHECK();
-  k_backsub<<<(int)(((int64_t)pv.m * 32 + 255) / 256), 256, 0, s>>>(pv, cv, so ? 0 : 1); BA_LAUNCH_CHECK();
-  BA_MARK(pl, BA_STAGE_RETR, s);
-  if (so) {
-    BA_CUDA(cudaMemcpyAsync(pb->poses_out, pb->poses, (size_t)pv.N * 7 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  } else {
-    k_pose_retr<<<(pv.N + 127) / 128, 128, 0, s>>>(cv, pv.N); BA_LAUNCH_CHECK();
+  {
+    const int nb_back = (int)(((int64_t)pv.m * 32 + 255) / 256), nb_retr = so ? 0 : (pv.N + 255) / 256;
+    k_backsub<<<nb_back + nb_retr, 256, 0, s>>>(pv, cv, so ? 0 : 1, nb_back, so ? 0 : pv.N); BA_LAUNCH_CHECK();
   }
+  BA_MARK(pl, BA_STAGE_RETR, s);
+  if (so) BA_CUDA(cudaMemcpyAsync(pb->poses_out, pb->poses, (size_t)pv.N * 7 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   BA_MARK(pl, BA_N_STAGES, s);
   return BA_OK;
 }

@@ -109,7 +109,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
   const int M = cv.M, bw = cv.bw, ld = cv.ld, off = cv.off;
   const int NT8 = (M + 7) >> 3, Mp = NT8 * 8;
   const int side = twist ? (int)blockIdx.x : 0;
-  const int Jm0 = (NT8 - 16) / 2, Jm1 = NT8 - 16 - Jm0;             // columns eliminated from the top / from the bottom
+  // columns eliminated from the top / from the bottom: equal shares, because the 16 middle columns can only start
+  // once BOTH sides are done (measured: giving side 0 fewer columns to balance its extra middle work is slower)
+  const int Jm0 = (NT8 - 16) / 2, Jm1 = NT8 - 16 - Jm0;
   const int c1 = twist ? (side ? Jm1 : Jm0) : NT8;                  // end of this side's first segment
   const int NTloc = twist ? c1 + 16 : NT8;                          // tiles this side ever sees (local coordinates)
   const int nseg = (twist && side == 0) ? 2 : 1;
