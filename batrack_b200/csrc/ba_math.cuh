@@ -161,8 +161,8 @@ struct EdgeTerms {
 // fast reciprocal / reciprocal square root on the device (a few ulp; the per-edge terms are fp32 anyway and
 // parity is judged at 1e-4 against fp64), exact forms on the host
 #ifdef __CUDA_ARCH__
-BA_HD float ba_rcp(float x) { return __frcp_rn(x); }
-BA_HD float ba_rsqrt(float x) { return rsqrtf(x); }
+BA_HD float ba_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }      // 1 ulp
+BA_HD float ba_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }  // 2 ulp
 #else
 BA_HD float ba_rcp(float x) { return 1.0f / x; }
 BA_HD float ba_rsqrt(float x) { return 1.0f / sqrtf(x); }
