@@ -36,6 +36,7 @@ SYMBOLS = {
     "ba_plan_set_layout": (C.c_int, [_P, _I32, _I32]),
     "ba_plan_tracks": (C.c_int, [_P, _P, _P]),
     "ba_step": (C.c_int, [_P, C.POINTER(BaProblem), _P]),
+    "ba_update": (C.c_int, [_P, C.POINTER(BaProblem), _P, _I32, _P]),
     "ba_assemble": (C.c_int, [_P, C.POINTER(BaProblem), _P]),
     "ba_plan_reduced_system": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_I64)]),
     "ba_solve_update": (C.c_int, [_P, C.POINTER(BaProblem), _P]),

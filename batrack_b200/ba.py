@@ -123,3 +123,28 @@ def BA(poses, patches, intrinsics, targets, weights, lmbda, ii, jj, kk, bounds, 
     """One damped Gauss-Newton step without the prior (ba.py:103-213)."""
     return _run(poses, patches, None, intrinsics, targets, weights, lmbda, ii, jj, kk, bounds, ep, PRINT, fixedp,
                 structure_only, loss, 0.0, group, plan)
+
+
+def BA_update(poses, patches, patches_monodisp, intrinsics, targets_2d, weights_pose, weights, lmbda, ii, jj, kk, bounds,
+              ep=10.0, fixedp=1, loss='huber', alpha=0.05, iters=4, plan=None):
+    """The BA driver loop of BATRACK.update (main/batrack.py:869-875) as ONE native call:
+    `iters` x { BA_rgbd_droid(weights_pose, structure_only=False); BA_rgbd_droid(weights, structure_only=True) },
+    sharing the topology plan, the workspace and the launch stream, with no Python between the 2*iters steps.
+    Equivalent to calling BA_rgbd_droid in that order; returns the final (SE3 poses, patches)."""
+    pdata = poses.data
+    if not pdata.is_cuda:
+        raise RuntimeError("batrack_b200 runs on CUDA tensors only; there is no CPU fallback")
+    if plan is None:
+        plan = get_plan(ii, jj, kk, pdata.shape[1], patches.shape[1])
+    prob, poses_out, patches_out, keep = _problem(plan, poses, patches, patches_monodisp, intrinsics, targets_2d,
+                                                  weights_pose, lmbda, bounds, ep, fixedp, False, loss, alpha)
+    E = plan.info.n_edges
+    w_all = _capi.require_cuda_f32("weights", weights, contiguous=False)
+    if tuple(w_all.shape) != (1, E, 2):
+        raise ValueError(f"weights: expected shape {(1, E, 2)}, got {tuple(w_all.shape)}")
+    w_all = w_all.contiguous()
+    with torch.cuda.device(pdata.device):
+        _capi.check(_capi.lib().ba_update(plan.handle, C.byref(prob), _capi.ptr(w_all), int(iters),
+                                          _capi.stream_ptr(pdata.device)), "ba_update")
+    del keep
+    return SE3(poses_out), patches_out

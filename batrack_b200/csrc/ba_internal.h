@@ -90,6 +90,7 @@ struct BaPlan {
   int64_t sy_floats;                   // capacity of SY (elements)
   int64_t est_floats;                  // size of Est
   int last_n, last_fixedp;             // layout of the last ba_assemble
+  float *pp_buf[2];                    // ping-pong (poses | patches) buffers of ba_update
   // staging buffers of ba_step_host
   void *host_stage;
   size_t host_stage_bytes;

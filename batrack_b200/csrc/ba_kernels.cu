@@ -993,6 +993,35 @@ extern "C" int ba_step(BaPlan *pl, const BaProblem *pb, void *stream) {
   return ba_solve_update(pl, pb, stream);
 }
 
+extern "C" int ba_update(BaPlan *pl, const BaProblem *pb, const float *weights_all, int32_t iters, void *stream) {
+  if (!pl || !pb || !weights_all || iters <= 0 || !pb->poses_out || !pb->patches_out) return BA_ERR_ARG;
+  const size_t np = (size_t)pl->v.N * 7, nq = (size_t)pl->v.NM * 3;
+  if (!pl->pp_buf[0]) {
+    for (int k = 0; k < 2; ++k) {
+      void *q = nullptr;
+      BA_CUDA(cudaMalloc(&q, (np + nq + 8) * sizeof(float)));
+      pl->owned.push_back(q);
+      pl->pp_buf[k] = (float *)q;
+    }
+  }
+  BaProblem cur = *pb;
+  const int total = 2 * iters;
+  for (int c = 0; c < total; ++c) {
+    const bool last = c == total - 1;
+    float *po = last ? pb->poses_out : pl->pp_buf[c & 1];
+    float *qo = last ? pb->patches_out : pl->pp_buf[c & 1] + np;
+    cur.poses_out = po;
+    cur.patches_out = qo;
+    cur.structure_only = c & 1;                        // main/batrack.py:871-872 then :874-875
+    cur.weights = (c & 1) ? weights_all : pb->weights;
+    int rc = ba_step(pl, &cur, stream);
+    if (rc) return rc;
+    cur.poses = po;
+    cur.patches = qo;
+  }
+  return BA_OK;
+}
+
 extern "C" int ba_plan_debug_dense(const BaPlan *pl, int32_t n, float *S, float *y, float *dX, float *Q,
                                    float *w, float *dZ, void *stream_) {
   if (!pl || pl->last_fixedp < 0) return BA_ERR_ARG;

@@ -343,6 +343,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
   pl->last_n = pl->last_fixedp = -1;
   pl->host_stage = nullptr;
   pl->host_stage_bytes = 0;
+  pl->pp_buf[0] = pl->pp_buf[1] = nullptr;
   pl->timing = 0;
   pl->ev_mask = 0;
   for (auto &e : pl->ev) e = nullptr;

@@ -86,6 +86,49 @@ __device__ __forceinline__ long long clk_after(double dep) { long long t; asm vo
 __device__ __forceinline__ long long clk_after(int dep) { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep)); return t; }
 #define BA_TRD(slot, dep) do { if (trace && lane == 0) trace[(size_t)J * 16 + (slot)] = clk_after(dep); } while (0)
 
+// Step tables of the solver (which operand tiles every register tile needs when circular position e leaves the
+// window, which two tiles of a warp touch e, and the other position of those tiles). They depend on nothing but
+// the tile ownership, so they are built once per process into global memory and copied to shared memory by
+// every launch. Layout: tabU [16][136], tabP [16][8], tabX [16][8].
+__global__ void k_build_step_tables(unsigned *gtab) {
+  const int tau = threadIdx.x;
+  constexpr int kMmaThreadsLocal = 256;
+  unsigned *tabU = gtab, *tabP = gtab + 16 * 136, *tabX = tabP + 16 * 8;
+  for (int o = tau; o < 16 * 136; o += kMmaThreadsLocal) {
+    const int e = o / 136, idx = o - e * 136;
+    const int x = c_px[idx], y = c_py[idx];
+    unsigned offA = 16 * kTs, offB = 16 * kTs;                      // inactive tile: both operands = the zero tile
+    if (x != e && y != e) {
+      const int ax = (x - e) & 15, ay = (y - e) & 15;
+      offA = (ax > ay ? x : y) * kTs;                               // row tile = larger global index
+      offB = (ax > ay ? y : x) * kTs;
+    }
+    // bits 0-11 offA, 12-23 offB, 24 this pair touches e (+25: which of the warp's two), 26 it touches e+1 (+27)
+    const int w = idx & 7, en = (e + 1) & 15;
+    unsigned fl = 0;
+    int ke = 0, kn = 0;
+    for (int t2 = 0; t2 < idx / 8; ++t2) {
+      const int x2 = c_px[t2 * 8 + w], y2 = c_py[t2 * 8 + w];
+      ke += (x2 == e || y2 == e);
+      kn += (x2 == en || y2 == en);
+    }
+    if (x == e || y == e) fl |= 1u | ((unsigned)ke << 1);
+    if (x == en || y == en) fl |= 4u | ((unsigned)kn << 3);
+    tabU[o] = offA | (offB << 12) | (fl << 24);
+  }
+  for (int o = tau; o < 16 * 8; o += kMmaThreadsLocal) {
+    const int e = o >> 3, w = o & 7;
+    unsigned m = 0, xo = 0;
+    int k = 0;
+    for (int t = 0; t < kTilesPerWarp; ++t) {
+      const int x = c_px[t * 8 + w], y = c_py[t * 8 + w];
+      if (x == e || y == e) { m |= 1u << t; xo |= (unsigned)(x == e ? y : x) << (8 * k++); }
+    }
+    tabP[o] = m;
+    tabX[o] = xo;
+  }
+}
+
 // cluster-wide barrier (both CTAs of the twisted factorisation); release/acquire orders global memory
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -100,6 +143,7 @@ __device__ __forceinline__ void cluster_sync() {
 __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, int allow_retry, double *__restrict__ Wg_all,
                                                                    double *__restrict__ L_all, double *__restrict__ XD,
                                                                    int *__restrict__ gfl, int twist,
+                                                                   const unsigned *__restrict__ gtab,
                                                                    long long *__restrict__ trace) {
   extern __shared__ double dsm[];
   const int tau = threadIdx.x, lane = tau & 31, hw = tau >> 5;
@@ -137,40 +181,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
   auto Sg = [&](int r, int c) { return (size_t)r * ld + c + off; };
   int status = 0;
 
-  // ---- step tables: which operand tiles every register tile needs when position e leaves the window ----
-  for (int o = tau; o < 16 * 136; o += kMmaThreads) {
-    const int e = o / 136, idx = o - e * 136;
-    const int x = c_px[idx], y = c_py[idx];
-    unsigned offA = 16 * kTs, offB = 16 * kTs;                      // inactive tile: both operands = the zero tile
-    if (x != e && y != e) {
-      const int ax = (x - e) & 15, ay = (y - e) & 15;
-      offA = (ax > ay ? x : y) * kTs;                               // row tile = larger global index
-      offB = (ax > ay ? y : x) * kTs;
-    }
-    // bits 0-11 offA, 12-23 offB, 24 this pair touches e (+25: which of the warp's two), 26 it touches e+1 (+27)
-    const int w = idx & 7, en = (e + 1) & 15;
-    unsigned fl = 0;
-    int ke = 0, kn = 0;
-    for (int t2 = 0; t2 < idx / 8; ++t2) {
-      const int x2 = c_px[t2 * 8 + w], y2 = c_py[t2 * 8 + w];
-      ke += (x2 == e || y2 == e);
-      kn += (x2 == en || y2 == en);
-    }
-    if (x == e || y == e) fl |= 1u | ((unsigned)ke << 1);
-    if (x == en || y == en) fl |= 4u | ((unsigned)kn << 3);
-    tabU[o] = offA | (offB << 12) | (fl << 24);
-  }
-  for (int o = tau; o < 16 * 8; o += kMmaThreads) {
-    const int e = o >> 3, w = o & 7;
-    unsigned m = 0, xo = 0;
-    int k = 0;
-    for (int t = 0; t < kTilesPerWarp; ++t) {
-      const int x = c_px[t * 8 + w], y = c_py[t * 8 + w];
-      if (x == e || y == e) { m |= 1u << t; xo |= (unsigned)(x == e ? y : x) << (8 * k++); }
-    }
-    tabP[o] = m;
-    tabX[o] = xo;
-  }
+  // ---- step tables (static, built once per process by k_build_step_tables): global -> shared ----
+  for (int o = tau; o < 16 * 136 + 2 * 16 * 8; o += kMmaThreads) tabU[o] = gtab[o];
   for (int o = tau; o < kTs; o += kMmaThreads) { Psm[16 * kTs + o] = 0.0; Nsm[16 * kTs + o] = 0.0; }
 
   for (int attempt = 0; attempt < 2; ++attempt) {
@@ -616,7 +628,11 @@ int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, 
   static long long *trace = nullptr;
   static int trace_left = 0;
   static int twist_min = 64;
+  static unsigned *gtab = nullptr;
   if (!attr_set) {
+    BA_CUDA(cudaMalloc(&gtab, (16 * 136 + 2 * 16 * 8) * sizeof(unsigned)));
+    k_build_step_tables<<<1, 256, 0, s>>>(gtab);
+    BA_LAUNCH_CHECK();
     BA_CUDA(cudaFuncSetAttribute(k_solve_band_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
     if (const char *e = getenv("BA_TRACE")) { trace_left = atoi(e); BA_CUDA(cudaMalloc(&trace, 16 * 8 * 4096)); }
     if (const char *e = getenv("BA_TWIST_MIN")) twist_min = atoi(e);        // tile columns from which two CTAs are used
@@ -641,7 +657,7 @@ int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, 
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  BA_CUDA(cudaLaunchKernelEx(&cfg, k_solve_band_mma, cv, allow_retry, W_all, L_all, XD, gfl, twist, tr ? trace : (long long *)nullptr));
+  BA_CUDA(cudaLaunchKernelEx(&cfg, k_solve_band_mma, cv, allow_retry, W_all, L_all, XD, gfl, twist, (const unsigned *)gtab, tr ? trace : (long long *)nullptr));
   BA_LAUNCH_CHECK();
   if (tr && --trace_left == 0) {       // debug only: synchronises and prints mean phase lengths in SM cycles
     std::vector<long long> h((size_t)nt * 16);

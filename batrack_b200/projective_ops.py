@@ -56,3 +56,9 @@ def flow_mag(poses, patches, intrinsics, ii, jj, kk, beta=0.3):
     c1 = transform(poses, patches, intrinsics, ii, jj, kk, tonly=False)
     c2 = transform(poses, patches, intrinsics, ii, jj, kk, tonly=True)
     return beta * (c1 - c0).norm(dim=-1) + (1 - beta) * (c2 - c0).norm(dim=-1)
+
+
+def point_cloud(poses, patches, intrinsics, ix):
+    """projective_ops.py:107-109: back-projected patches in the world frame, [1, M, P, P, 4] homogeneous points
+    (x, y, z, inverse depth). SE3 inverse / action run in the library's SE3 kernels."""
+    return poses[:, ix, None, None].inv() * iproj(patches, intrinsics[:, ix])

@@ -164,17 +164,27 @@ def davis_like_update(dev, reps=20):
                                      loss=ps.loss, alpha=ps.alpha)
         return G, p
 
-    for _ in range(3):
-        update()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        update()
-    e1.record()
-    torch.cuda.synchronize()
+    from batrack_b200.ba import BA_update
+
+    def update_fused():
+        return BA_update(SE3(t["poses"]), t["patches"], t["patches_monodisp"], t["intrinsics"], t["targets_2d"], w_pose,
+                         w_full, ps.lmbda, t["ii"], t["jj"], t["kk"], ps.bounds, ep=ps.ep, fixedp=ps.fixedp,
+                         loss=ps.loss, alpha=ps.alpha, iters=4)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
     return {"edges": ps.E, "free_poses": int(max(ps.ii.max(), ps.jj.max())) + 1 - ps.fixedp, "ba_calls_per_update": 8,
-            "ms_per_update": e0.elapsed_time(e1) / reps}
+            "ms_per_update": timed(update), "ms_per_update_fused_call": timed(update_fused)}
 
 
 def main():

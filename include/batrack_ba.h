@@ -106,6 +106,13 @@ int ba_plan_tracks(const BaPlan *plan, int32_t *kx_out /* device, m ints */, voi
 /* One full BA call on one device: assemble -> Schur -> solve -> back-substitute -> retract. */
 int ba_step(BaPlan *plan, const BaProblem *prob, void *stream);
 
+/* The BA driver loop of BATRACK.update (main/batrack.py:869-875) in one call: `iters` times
+ *   { pose + depth step on prob->weights (weights_pose), depth-only step on weights_all (weights) },
+ * each step consuming the previous step's poses / patches. prob->structure_only is ignored; results of the
+ * last step land in prob->poses_out / patches_out. Intermediate states live in plan-owned buffers; the
+ * topology plan, the workspace and every launch are shared by the 2*iters steps. */
+int ba_update(BaPlan *plan, const BaProblem *prob, const float *weights_all, int32_t iters, void *stream);
+
 /* First half: residuals, Jacobians, per-track Schur complement. Leaves the (partial) reduced camera
  * system in the plan's exchange buffer [S | y] (see ba_plan_reduced_system). No-op for
  * structure-only calls apart from the per-track C, w. */

@@ -286,3 +286,58 @@ def test_structure_only_and_ba_variant_on_mid_graph():
         ep, ed = rel_err(P, P64), rel_err(D, D64)
         print(f"\nmid {variant} [so, full, so]: poses {ep:.2e} disps {ed:.2e}")
         assert ep < TOL and ed < TOL
+
+
+def test_fused_update_equals_call_sequence():
+    """BA_update (one native call for the loop of main/batrack.py:869-875) against the same steps issued one by one
+    and against the fp64 oracle."""
+    from batrack_b200 import synth
+    from batrack_b200.ba import BA_update
+    from batrack_b200.lietorch import SE3
+    from gpu_util import as_cuda, run_ours
+    ps, w_all = synth.make_slam_problem(n_frames=21, patches_per_frame=64, seed=11)
+    t = as_cuda(ps)
+    wp = torch.from_numpy(ps.weights).cuda()[None]
+    wa = torch.from_numpy(w_all).cuda()[None]
+    G, p = BA_update(SE3(t["poses"]), t["patches"], t["patches_monodisp"], t["intrinsics"], t["targets_2d"], wp, wa,
+                     ps.lmbda, t["ii"], t["jj"], t["kk"], ps.bounds, ep=ps.ep, fixedp=ps.fixedp, loss=ps.loss,
+                     alpha=ps.alpha, iters=3)
+    ws, so = [ps.weights, w_all] * 3, [False, True] * 3
+    P, D = run_ours(ps, ws, so)
+    P64, D64 = _oracle().run_sequence(ps, ws, so, torch.float64, mode="sparse")
+    assert rel_err(G.data[0].cpu().numpy(), P[-1]) < 2e-6 and rel_err(p[0, :, 2, 0, 0].cpu().numpy(), D[-1]) < 2e-5
+    assert rel_err(G.data[0].cpu().numpy(), P64[-1]) < TOL and rel_err(p[0, :, 2, 0, 0].cpu().numpy(), D64[-1]) < TOL
+
+
+def test_point_cloud_and_flow_mag_match_oracle():
+    """The reprojection consumers next to BA (main/batrack.py:891-893, 1011-1018)."""
+    from batrack_b200 import projective_ops as pops, synth
+    from batrack_b200.lietorch import SE3
+    from gpu_util import as_cuda
+    from oracle import se3_ops
+    ps, _ = synth.make_slam_problem(n_frames=21, patches_per_frame=32, seed=3)
+    t = as_cuda(ps)
+    NM = ps.patches.shape[0]
+    ix = torch.arange(NM, device="cuda") // 32
+    pc = pops.point_cloud(SE3(t["poses"]), t["patches"], t["intrinsics"], ix)
+    f = lambda a: torch.from_numpy(a).double()
+    P, X, K = f(ps.poses), f(ps.patches), f(ps.intrinsics)
+    ixc = ix.cpu()
+    x0 = torch.stack([(X[:, 0] - K[ixc, 2]) / K[ixc, 0], (X[:, 1] - K[ixc, 3]) / K[ixc, 1], torch.ones(NM, dtype=torch.float64), X[:, 2]], 1)
+    ref = se3_ops.se3_act4(se3_ops.se3_inv(P[ixc].contiguous()), x0)
+    assert rel_err(pc[0, :, 0, 0].cpu().numpy(), ref.numpy()) < 2e-6
+    fm = pops.flow_mag(SE3(t["poses"]), t["patches"], t["intrinsics"], t["ii"], t["jj"], t["kk"], beta=0.5)
+    g = lambda a: torch.from_numpy(a).long()
+    c0, *_ = _oracle().reproject_with_jacobians(P, X, K, g(ps.ii), g(ps.ii), g(ps.kk))
+    c1, *_ = _oracle().reproject_with_jacobians(P, X, K, g(ps.ii), g(ps.jj), g(ps.kk))
+    Pt = P.clone()                                                    # tonly: rotation of Gij dropped (projective_ops.py:63-64)
+    Gij = se3_ops.se3_mul(P[g(ps.jj)].contiguous(), se3_ops.se3_inv(P[g(ps.ii)].contiguous()))
+    Gij[:, 3:] = torch.tensor([0, 0, 0, 1.0])
+    xk = X[g(ps.kk)]
+    Ki, Kj = K[g(ps.ii)], K[g(ps.jj)]
+    X0 = torch.stack([(xk[:, 0] - Ki[:, 2]) / Ki[:, 0], (xk[:, 1] - Ki[:, 3]) / Ki[:, 1], torch.ones(len(xk), dtype=torch.float64), xk[:, 2]], 1)
+    X1 = se3_ops.se3_act4(Gij, X0)
+    dcl = 1.0 / X1[:, 2].clamp(min=1e-2)
+    c2 = torch.stack([Kj[:, 0] * dcl * X1[:, 0] + Kj[:, 2], Kj[:, 1] * dcl * X1[:, 1] + Kj[:, 3]], 1)
+    ref_fm = 0.5 * (c1 - c0).norm(dim=1) + 0.5 * (c2 - c0).norm(dim=1)
+    assert np.abs(fm[0, :, 0, 0].cpu().numpy() - ref_fm.numpy()).max() < 2e-3     # pixels; fp32 coordinates ~1e3
