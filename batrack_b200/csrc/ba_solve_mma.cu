@@ -180,6 +180,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
   const double ep = (double)cv.ep;
   auto Sg = [&](int r, int c) { return (size_t)r * ld + c + off; };
   int status = 0;
+  long long *phase = trace ? trace + 16 * 4096 + side * 8 : nullptr;   // coarse phase stamps of this side (BA_TRACE)
+  if (side) trace = nullptr;                                           // per-column stamps: side 0 only
+  if (phase && tau == 0) phase[0] = clock64();
 
   // ---- step tables (static, built once per process by k_build_step_tables): global -> shared ----
   for (int o = tau; o < 16 * 136 + 2 * 16 * 8; o += kMmaThreads) tabU[o] = gtab[o];
@@ -491,6 +494,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
     }
     __syncthreads();
     (void)failed;
+    if (phase && tau == 0) phase[1] = clock64();
     const bool bad = s_fail || s_abort;                             // this side could not factor (or was told to stop)
     const int ncols = (twist && side == 1) ? c1 : NTloc;            // tile columns of L (and W_J) this side owns
 
@@ -587,6 +591,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
       anybad = true;
     }
     __syncthreads();
+    if (phase && tau == 0) phase[2] = clock64();
     // ---- write this side's rows of dX (zeros if any factorisation failed, ba.py:12-13), NaN check ----
     const int nrows = 8 * ((twist && side == 1) ? c1 : NTloc);
     int nan_local = 0;
@@ -608,6 +613,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
     break;
   }
   if (tau == 0 && side == 0) cv.status[0] = status;
+  if (phase && tau == 0) phase[3] = clock64();
 }
 
 size_t solve_mma_smem_bytes(int M) {
@@ -634,7 +640,7 @@ int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, 
     k_build_step_tables<<<1, 256, 0, s>>>(gtab);
     BA_LAUNCH_CHECK();
     BA_CUDA(cudaFuncSetAttribute(k_solve_band_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
-    if (const char *e = getenv("BA_TRACE")) { trace_left = atoi(e); BA_CUDA(cudaMalloc(&trace, 16 * 8 * 4096)); }
+    if (const char *e = getenv("BA_TRACE")) { trace_left = atoi(e); BA_CUDA(cudaMalloc(&trace, 16 * 8 * 4096 + 256)); }
     if (const char *e = getenv("BA_TWIST_MIN")) twist_min = atoi(e);        // tile columns from which two CTAs are used
     attr_set = true;
   }
@@ -643,7 +649,7 @@ int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, 
   double *L_all = scratch, *W_all = L_all + 2 * Mp * (cv.bw + 1), *XD = W_all + 2 * (Mp / 8) * 64;
   int *gfl = reinterpret_cast<int *>(XD + 128 * 128 + 256);
   const int twist = nt >= twist_min ? 1 : 0;
-  const bool tr = trace && trace_left > 0 && nt <= 4096 && !twist;
+  const bool tr = trace && trace_left > 0 && nt <= 4096;
   BA_CUDA(cudaMemsetAsync(gfl, 0, 8 * sizeof(int), s));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(twist ? 2 : 1);
@@ -660,19 +666,25 @@ int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, 
   BA_CUDA(cudaLaunchKernelEx(&cfg, k_solve_band_mma, cv, allow_retry, W_all, L_all, XD, gfl, twist, (const unsigned *)gtab, tr ? trace : (long long *)nullptr));
   BA_LAUNCH_CHECK();
   if (tr && --trace_left == 0) {       // debug only: synchronises and prints mean phase lengths in SM cycles
-    std::vector<long long> h((size_t)nt * 16);
+    std::vector<long long> h((size_t)16 * 4096 + 32);
     BA_CUDA(cudaStreamSynchronize(s));
     BA_CUDA(cudaMemcpy(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost));
     double d[8] = {0};
-    for (int J = 1; J + 1 < nt; ++J) {
+    const int ncol = twist ? (nt - 16) / 2 : nt;                       // side 0, first segment
+    for (int J = 1; J + 1 < ncol; ++J) {
       const long long *a = &h[(size_t)J * 16], *n = &h[(size_t)(J + 1) * 16];
       d[0] += a[1] - a[0]; d[1] += a[2] - a[1]; d[2] += a[3] - a[2]; d[3] += a[4] - a[3]; d[4] += a[5] - a[4];
       d[5] += n[0] - a[5]; d[6] += a[9] - a[8]; d[7] += a[10] - a[9];
     }
-    const double k = nt - 2;
+    const double k = ncol - 2;
+    for (int sd = 0; sd < (twist ? 2 : 1); ++sd) {
+      const long long *ph = &h[(size_t)16 * 4096 + sd * 8];
+      fprintf(stderr, "[BA_TRACE] side %d: factor+forward %lld  back-substitution %lld  tail %lld cycles\n", sd,
+              ph[1] - ph[0], ph[2] - ph[1], ph[3] - ph[2]);
+    }
     fprintf(stderr, "[BA_TRACE] tiles %d | tile warp 0: extract %.0f waitW %.0f P %.0f waitP %.0f U %.0f refill %.0f | "
             "factor warp: waitD %.0f A %.0f | step %.0f cycles\n", nt, d[0] / k, d[1] / k, d[2] / k, d[3] / k, d[4] / k,
-            d[5] / k, d[6] / k, d[7] / k, (double)(h[(size_t)(nt - 1) * 16] - h[16]) / k);
+            d[5] / k, d[6] / k, d[7] / k, (double)(h[(size_t)(ncol - 1) * 16] - h[16]) / k);
   }
   return BA_OK;
 }
