@@ -45,6 +45,8 @@ SYMBOLS = {
     "ba_plan_enable_timing": (C.c_int, [_P, C.c_int]),
     "ba_plan_last_timing": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "ba_step_host": (C.c_int, [_P, C.POINTER(BaProblem), _P]),
+    "ba_step_host_async": (C.c_int, [_P, C.POINTER(BaProblem), _P]),
+    "ba_host_sync": (C.c_int, [_P, _P, C.c_int]),
     "ba_reproject": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P]),
     "se3_expm": (C.c_int, [_P, _P, _I64, _P]),
     "se3_logm": (C.c_int, [_P, _P, _I64, _P]),

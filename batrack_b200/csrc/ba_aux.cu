@@ -120,13 +120,43 @@ extern "C" int ba_reproject(const float *poses, const float *patches, const floa
   return BA_OK;
 }
 
-// Host buffers in, host buffers out: the per-call inputs (poses, patches, monodisp, intrinsics,
-// targets, weights, lmbda_vec) are copied to a plan-owned device staging block, ba_step runs, the
-// two results are copied back, and the stream is synchronised. Indices live in the plan already.
-extern "C" int ba_step_host(BaPlan *pl, const BaProblem *ph, void *stream_) {
+// ---- host-buffer entry points -------------------------------------------------------------------
+// The per-call inputs (poses, patches, monodisp, intrinsics, targets, weights, lmbda_vec) are HOST arrays;
+// they are copied into one of two plan-owned device staging slots, ba_step runs on the caller's stream, and the
+// two results are copied back. Indices live in the plan already. The copies run on the plan's own H2D / D2H
+// streams, so that the upload of call k+1 and the download of call k-1 overlap the kernels of call k (with
+// pinned host memory); consecutive calls serialise on the caller's stream because they share the workspace.
+namespace {
+struct HostPipe {
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t in_ready[2] = {nullptr, nullptr}, computed[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+  char *stage[2] = {nullptr, nullptr};
+  size_t bytes = 0;
+  unsigned long long seq = 0;
+};
+
+void host_pipe_destroy(void *p_) {
+  HostPipe *p = static_cast<HostPipe *>(p_);
+  if (!p) return;
+  if (p->h2d) cudaStreamSynchronize(p->h2d);
+  if (p->d2h) cudaStreamSynchronize(p->d2h);
+  for (int k = 0; k < 2; ++k) {
+    if (p->stage[k]) cudaFree(p->stage[k]);
+    if (p->in_ready[k]) cudaEventDestroy(p->in_ready[k]);
+    if (p->computed[k]) cudaEventDestroy(p->computed[k]);
+    if (p->out_done[k]) cudaEventDestroy(p->out_done[k]);
+  }
+  if (p->h2d) cudaStreamDestroy(p->h2d);
+  if (p->d2h) cudaStreamDestroy(p->d2h);
+  delete p;
+}
+}  // namespace
+
+extern "C" int ba_step_host_async(BaPlan *pl, const BaProblem *ph, void *stream_) {
   if (!pl || !ph || !ph->poses || !ph->patches || !ph->intrinsics || !ph->targets || !ph->weights ||
       !ph->poses_out || !ph->patches_out)
     return BA_ERR_ARG;
+  if (ph->targets_stride != 0 && ph->targets_stride != 2) return BA_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream_;
   const size_t N = pl->v.N, NM = pl->v.NM, E = (size_t)pl->v.E, m = pl->v.m;
   const size_t f = sizeof(float);
@@ -135,32 +165,72 @@ extern "C" int ba_step_host(BaPlan *pl, const BaProblem *ph, void *stream_) {
                o_intr = o_mono + up(NM * f), o_tg = o_intr + up(4 * N * f), o_w = o_tg + up(2 * E * f),
                o_lam = o_w + up(2 * E * f), o_pout = o_lam + up(m * f), o_qout = o_pout + up(7 * N * f),
                total = o_qout + up(3 * NM * f);
-  if (pl->host_stage_bytes < total) {
-    if (pl->host_stage) BA_CUDA(cudaFree(pl->host_stage));
-    pl->host_stage = nullptr;
-    BA_CUDA(cudaMalloc(&pl->host_stage, total));
-    pl->host_stage_bytes = total;
+  HostPipe *hp = static_cast<HostPipe *>(pl->host_pipe);
+  if (!hp) {
+    hp = new HostPipe();
+    pl->host_pipe = hp;
+    pl->host_pipe_destroy = host_pipe_destroy;
+    BA_CUDA(cudaStreamCreateWithFlags(&hp->h2d, cudaStreamNonBlocking));
+    BA_CUDA(cudaStreamCreateWithFlags(&hp->d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      BA_CUDA(cudaEventCreateWithFlags(&hp->in_ready[k], cudaEventDisableTiming));
+      BA_CUDA(cudaEventCreateWithFlags(&hp->computed[k], cudaEventDisableTiming));
+      BA_CUDA(cudaEventCreateWithFlags(&hp->out_done[k], cudaEventDisableTiming));
+    }
+    BA_CUDA(cudaMalloc((void **)&hp->stage[0], total));
+    BA_CUDA(cudaMalloc((void **)&hp->stage[1], total));
+    hp->bytes = total;
   }
-  char *d = (char *)pl->host_stage;
+  if (hp->bytes < total) return BA_ERR_ARG;            // the plan fixes N, NM, E, m: cannot happen
+  const int slot = (int)(hp->seq & 1);
+  char *d = hp->stage[slot];
+  if (hp->seq >= 2) BA_CUDA(cudaStreamWaitEvent(hp->h2d, hp->computed[slot], 0));   // inputs of call seq-2 consumed
   BaProblem pd = *ph;
 #define H2D(field, off, bytes)                                                                          \
-  do { BA_CUDA(cudaMemcpyAsync(d + (off), ph->field, (bytes), cudaMemcpyHostToDevice, s));              \
+  do { BA_CUDA(cudaMemcpyAsync(d + (off), ph->field, (bytes), cudaMemcpyHostToDevice, hp->h2d));        \
        pd.field = (const float *)(d + (off)); } while (0)
   H2D(poses, o_pose, 7 * N * f);
   H2D(patches, o_pat, 3 * NM * f);
   if (ph->monodisp) H2D(monodisp, o_mono, NM * f);
   H2D(intrinsics, o_intr, 4 * N * f);
-  if (ph->targets_stride != 0 && ph->targets_stride != 2) return BA_ERR_ARG;
   H2D(targets, o_tg, 2 * E * f);
   H2D(weights, o_w, 2 * E * f);
   if (ph->lmbda_vec) H2D(lmbda_vec, o_lam, m * f);
 #undef H2D
+  pd.targets_stride = 2;
+  BA_CUDA(cudaEventRecord(hp->in_ready[slot], hp->h2d));
+  BA_CUDA(cudaStreamWaitEvent(s, hp->in_ready[slot], 0));
+  if (hp->seq >= 2) BA_CUDA(cudaStreamWaitEvent(s, hp->out_done[slot], 0));          // results of call seq-2 downloaded
   pd.poses_out = (float *)(d + o_pout);
   pd.patches_out = (float *)(d + o_qout);
   int rc = ba_step(pl, &pd, stream_);
   if (rc) return rc;
-  BA_CUDA(cudaMemcpyAsync(ph->poses_out, pd.poses_out, 7 * N * f, cudaMemcpyDeviceToHost, s));
-  BA_CUDA(cudaMemcpyAsync(ph->patches_out, pd.patches_out, 3 * NM * f, cudaMemcpyDeviceToHost, s));
-  BA_CUDA(cudaStreamSynchronize(s));
+  BA_CUDA(cudaEventRecord(hp->computed[slot], s));
+  BA_CUDA(cudaStreamWaitEvent(hp->d2h, hp->computed[slot], 0));
+  BA_CUDA(cudaMemcpyAsync(ph->poses_out, pd.poses_out, 7 * N * f, cudaMemcpyDeviceToHost, hp->d2h));
+  BA_CUDA(cudaMemcpyAsync(ph->patches_out, pd.patches_out, 3 * NM * f, cudaMemcpyDeviceToHost, hp->d2h));
+  BA_CUDA(cudaEventRecord(hp->out_done[slot], hp->d2h));
+  hp->seq++;
   return BA_OK;
+}
+
+// Orders `stream` after the download of every call submitted so far (so an event recorded on it next sees the
+// results on the host); block != 0 also waits for it on the host.
+extern "C" int ba_host_sync(BaPlan *pl, void *stream_, int block) {
+  if (!pl) return BA_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream_;
+  HostPipe *hp = static_cast<HostPipe *>(pl->host_pipe);
+  if (hp && hp->seq > 0) {
+    BA_CUDA(cudaStreamWaitEvent(s, hp->out_done[(hp->seq - 1) & 1], 0));
+    if (hp->seq > 1) BA_CUDA(cudaStreamWaitEvent(s, hp->out_done[hp->seq & 1], 0));
+  }
+  if (block) BA_CUDA(cudaStreamSynchronize(s));
+  return BA_OK;
+}
+
+// One call, synchronous: ba_step_host_async + wait.
+extern "C" int ba_step_host(BaPlan *pl, const BaProblem *ph, void *stream_) {
+  int rc = ba_step_host_async(pl, ph, stream_);
+  if (rc) return rc;
+  return ba_host_sync(pl, stream_, 1);
 }

@@ -91,9 +91,9 @@ struct BaPlan {
   int64_t est_floats;                  // size of Est
   int last_n, last_fixedp;             // layout of the last ba_assemble
   float *pp_buf[2];                    // ping-pong (poses | patches) buffers of ba_update
-  // staging buffers of ba_step_host
-  void *host_stage;
-  size_t host_stage_bytes;
+  // double-buffered staging / copy streams of ba_step_host[_async] (ba_aux.cu)
+  void *host_pipe;
+  void (*host_pipe_destroy)(void *);
   std::vector<void *> owned;           // every cudaMalloc'ed block, for ba_plan_destroy
   // optional per-stage timing (ba_plan_enable_timing)
   int timing;

@@ -341,8 +341,8 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
   pl->status = nullptr;
   pl->sy_floats = 0;
   pl->last_n = pl->last_fixedp = -1;
-  pl->host_stage = nullptr;
-  pl->host_stage_bytes = 0;
+  pl->host_pipe = nullptr;
+  pl->host_pipe_destroy = nullptr;
   pl->pp_buf[0] = pl->pp_buf[1] = nullptr;
   pl->timing = 0;
   pl->ev_mask = 0;
@@ -491,7 +491,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
 extern "C" void ba_plan_destroy(BaPlan *pl) {
   if (!pl) return;
   for (void *p : pl->owned) cudaFree(p);
-  if (pl->host_stage) cudaFree(pl->host_stage);
+  if (pl->host_pipe && pl->host_pipe_destroy) pl->host_pipe_destroy(pl->host_pipe);
   for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
   delete pl;
 }

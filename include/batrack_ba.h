@@ -150,8 +150,18 @@ int ba_plan_status_ptr(const BaPlan *plan, int32_t **dev_status);
 int ba_plan_enable_timing(BaPlan *plan, int enable);
 int ba_plan_last_timing(BaPlan *plan, float *ms_out /* host, BA_N_STAGES floats */);
 
-/* Host-buffer convenience for end-to-end timing: pinned or pageable HOST arrays in, results out;
- * H2D/D2H copies are issued on `stream` and the call returns after synchronising it. */
+/* Host-buffer entry points (what a host-side caller holding CPU arrays binds; bench.py's e2e leg).
+ * Every pointer of `prob_host` is a HOST array (pinned memory for copy/compute overlap; pageable works but
+ * serialises); targets_stride must be 2. Inputs go to one of two plan-owned device staging slots on the plan's
+ * own upload stream, ba_step runs on `stream`, results return on the plan's download stream: the upload of
+ * call k+1 and the download of call k-1 overlap the kernels of call k.
+ *   ba_step_host_async  enqueue one step and return; host inputs must stay untouched until the step's upload has
+ *                       run and the host outputs are valid only after ba_host_sync.
+ *   ba_host_sync        order `stream` after the download of every step submitted so far; block != 0 also waits
+ *                       on the host.
+ *   ba_step_host        one synchronous step (= async + blocking sync). */
+int ba_step_host_async(BaPlan *plan, const BaProblem *prob_host, void *stream);
+int ba_host_sync(BaPlan *plan, void *stream, int block);
 int ba_step_host(BaPlan *plan, const BaProblem *prob_host, void *stream);
 
 /* ---- reprojection without Jacobians --------------------------------------------------------- */

@@ -341,3 +341,39 @@ def test_point_cloud_and_flow_mag_match_oracle():
     c2 = torch.stack([Kj[:, 0] * dcl * X1[:, 0] + Kj[:, 2], Kj[:, 1] * dcl * X1[:, 1] + Kj[:, 3]], 1)
     ref_fm = 0.5 * (c1 - c0).norm(dim=1) + 0.5 * (c2 - c0).norm(dim=1)
     assert np.abs(fm[0, :, 0, 0].cpu().numpy() - ref_fm.numpy()).max() < 2e-3     # pixels; fp32 coordinates ~1e3
+
+
+def test_host_buffer_pipeline_equals_device_call():
+    """ba_step_host_async / ba_host_sync (pinned host arrays in and out, double-buffered staging): four pipelined
+    steps with different weights give bitwise what BA_rgbd_droid gives on device tensors; ba_step_host likewise."""
+    from batrack_b200 import synth
+    from batrack_b200.ba import BA_rgbd_droid
+    from batrack_b200.host import HostBA
+    from batrack_b200.lietorch import SE3
+    from batrack_b200.plan import Plan
+    from gpu_util import as_cuda
+    ps, w_all = synth.make_slam_problem(n_frames=21, patches_per_frame=64, seed=5)
+    t = as_cuda(ps)
+    N, NM = t["poses"].shape[1], t["patches"].shape[1]
+    plan = Plan(t["ii"], t["jj"], t["kk"], N, NM)
+    host = {k: t[k].cpu().pin_memory() for k in ("poses", "patches", "patches_monodisp", "intrinsics", "targets_2d")}
+    rng = np.random.default_rng(0)
+    ws = [torch.from_numpy((ps.weights * rng.uniform(0.5, 1.0, ps.weights.shape)).astype(np.float32))[None].pin_memory()
+          for _ in range(4)]
+    outs = [(torch.empty(1, N, 7).pin_memory(), torch.empty(1, NM, 3, 1, 1).pin_memory()) for _ in range(4)]
+    hba = HostBA(plan)
+    for w, (op, oq) in zip(ws, outs):
+        hba.submit(host["poses"], host["patches"], host["patches_monodisp"], host["intrinsics"], host["targets_2d"], w,
+                   ps.lmbda, ps.bounds, op, oq, ep=ps.ep, fixedp=ps.fixedp, structure_only=False, loss=ps.loss,
+                   alpha=ps.alpha)
+    hba.sync()
+    for w, (op, oq) in zip(ws, outs):
+        G, p = BA_rgbd_droid(SE3(t["poses"]), t["patches"], t["patches_monodisp"], t["intrinsics"], t["targets_2d"], None,
+                             w.cuda(), ps.lmbda, t["ii"], t["jj"], t["kk"], ps.bounds, ep=ps.ep, fixedp=ps.fixedp,
+                             structure_only=False, loss=ps.loss, alpha=ps.alpha, plan=plan)
+        # S / y are summed with fp64 atomics in a run-dependent order: equal to rounding, not bitwise
+        assert rel_err(op.numpy(), G.data.cpu().numpy()) < 1e-6
+        assert rel_err(oq.numpy(), p.cpu().numpy()) < 1e-6
+    with pytest.raises(RuntimeError):
+        hba.submit(t["poses"], host["patches"], host["patches_monodisp"], host["intrinsics"], host["targets_2d"], ws[0],
+                   ps.lmbda, ps.bounds, *outs[0])
