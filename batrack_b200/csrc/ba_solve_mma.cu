@@ -32,6 +32,10 @@ constexpr int kMmaWarps = 8;                 // tile warps
 // (Measured alternative: factor warp alone on scheduler 0 and 3+3+2 tile warps on the others: the factorisation
 // drops to 1.8k cycles but [U] rises to 3.1k, slower overall.)
 constexpr int kMmaThreads = 32 * (kMmaWarps + 1);
+// "isolated" launch shape: 12 hardware warps, of which warp 0 (alone on scheduler 0) is the factor warp, warps
+// 1-3, 5-7, 9-10 are the tile warps (3 + 3 + 2 on schedulers 1-3) and warps 4, 8, 11 exit at once — the dependent
+// DFMA chain of the 8x8 factorisation then never queues behind a 16-cycle DMMA on its scheduler's FP64 unit.
+constexpr int kMmaHwThreads = 32 * 12;
 constexpr int kTilesPerWarp = 17;
 constexpr int kBackStages = 4;     // tile rows of L in flight during the back substitution
 constexpr int kPs = 12;            // row stride (doubles) of the shared 8x8 tiles: conflict-free fragment loads
@@ -140,13 +144,19 @@ __device__ __forceinline__ void cluster_sync() {
 // then hands CTA 0 what its eliminations contributed to the 16 middle tile columns, CTA 0 finishes the
 // middle, solves it, and both back-substitute their side in parallel ("burn at both ends": the serial chain
 // of a banded Cholesky is halved). Exchange through global scratch XD + cluster barriers.
-__global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, int allow_retry, double *__restrict__ Wg_all,
+__global__ void __launch_bounds__(kMmaHwThreads, 1) k_solve_band_mma(CallView cv, int allow_retry, double *__restrict__ Wg_all,
                                                                    double *__restrict__ L_all, double *__restrict__ XD,
                                                                    int *__restrict__ gfl, int twist,
                                                                    const unsigned *__restrict__ gtab,
                                                                    long long *__restrict__ trace) {
   extern __shared__ double dsm[];
-  const int tau = threadIdx.x, lane = tau & 31, hw = tau >> 5;
+  const int lane = threadIdx.x & 31;
+  int hw = threadIdx.x >> 5;                                        // logical warp: 0..7 tile warps, 8 factor warp
+  if (blockDim.x == kMmaHwThreads) {
+    hw = (int)(0xf76f543f2108ull >> (4 * hw)) & 15;                        // {8,0,1,2,-,3,4,5,-,6,7,-}
+    if (hw == 15) return;
+  }
+  const int tau = 32 * hw + lane;
   const bool is_factor = hw == kMmaWarps, is_tile = hw < kMmaWarps;
   const int warp = hw;                                              // tile warp index 0..7 (meaningful if is_tile)
   const int g = lane >> 2, q = lane & 3;
@@ -470,12 +480,20 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_band_mma(CallView cv, 
             if (own_next && tn == 0) ot[0] = (ot[0] & 0xff000000u) | zo;
             if (own_next && tn == 1) ot[1] = (ot[1] & 0xff000000u) | zo;
           }
+          // two passes (k = 0..3, then k = 4..7): the 17 DMMAs of a pass are independent of each other, so the warp
+          // never sits on the 26-cycle DMMA -> DMMA dependency of one tile, and the operand loads of a pass are
+          // issued together ahead of its DMMAs
 #pragma unroll
-          for (int t = 0; t < kTilesPerWarp; ++t) {
-            const unsigned o = ot[t];
-            const double *A = An + (o & 0xfffu), *B = Bp + ((o >> 12) & 0xfffu);
-            dmma884(ct[t][0], ct[t][1], A[0], B[0], ct[t][0], ct[t][1]);
-            dmma884(ct[t][0], ct[t][1], A[4], B[4], ct[t][0], ct[t][1]);
+          for (int h = 0; h < 2; ++h) {
+            double fa[kTilesPerWarp], fb[kTilesPerWarp];
+#pragma unroll
+            for (int t = 0; t < kTilesPerWarp; ++t) {
+              const unsigned o = ot[t];
+              fa[t] = An[(o & 0xfffu) + 4 * h];
+              fb[t] = Bp[((o >> 12) & 0xfffu) + 4 * h];
+            }
+#pragma unroll
+            for (int t = 0; t < kTilesPerWarp; ++t) dmma884(ct[t][0], ct[t][1], fa[t], fb[t], ct[t][0], ct[t][1]);
           }
           // an e-tile's registers take its refill; a tile that touches position e+1 goes to the warp's slots
 #pragma unroll
@@ -634,6 +652,7 @@ int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, 
   static long long *trace = nullptr;
   static int trace_left = 0;
   static int twist_min = 64;
+  static int iso = 0;        // measured on B200 (cfg3): [A] 3322 -> 1870 cycles but [U] 2464 -> 3121 with 3 tile warps per scheduler: slower overall
   static unsigned *gtab = nullptr;
   if (!attr_set) {
     BA_CUDA(cudaMalloc(&gtab, (16 * 136 + 2 * 16 * 8) * sizeof(unsigned)));
@@ -642,6 +661,7 @@ int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, 
     BA_CUDA(cudaFuncSetAttribute(k_solve_band_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
     if (const char *e = getenv("BA_TRACE")) { trace_left = atoi(e); BA_CUDA(cudaMalloc(&trace, 16 * 8 * 4096 + 256)); }
     if (const char *e = getenv("BA_TWIST_MIN")) twist_min = atoi(e);        // tile columns from which two CTAs are used
+    if (const char *e = getenv("BA_SOLVE_ISO")) iso = atoi(e);              // 1: 12 hardware warps, factor warp alone on scheduler 0
     attr_set = true;
   }
   const size_t Mp = ((size_t)(cv.M + 7) / 8) * 8;
@@ -653,7 +673,7 @@ int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, 
   BA_CUDA(cudaMemsetAsync(gfl, 0, 8 * sizeof(int), s));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(twist ? 2 : 1);
-  cfg.blockDim = dim3(kMmaThreads);
+  cfg.blockDim = dim3(iso ? kMmaHwThreads : kMmaThreads);
   cfg.dynamicSmemBytes = solve_mma_smem_bytes(cv.M);
   cfg.stream = s;
   cudaLaunchAttribute at[1];
