@@ -10,7 +10,8 @@
 
 namespace ba {
 
-constexpr int kEdgeThreads = 256;     // CTA size of the edge pass
+constexpr int kEdgeThreads = 256;     // CTA size of the generic edge pass (irregular groups)
+constexpr int kEdge2Warps = 4;        // warps per CTA of the lane-per-track edge pass (32 tracks per warp)
 constexpr int kSchurThreads = 256;    // CTA size of the per-track Schur kernel
 constexpr int kSolveThreads = 1024;   // CTA size of the window Cholesky
 constexpr int kMaxWindow = 150;       // largest band window (bw + 1) the shared-memory solver holds (fp64)
@@ -20,7 +21,7 @@ constexpr int kMaxWindow = 150;       // largest band window (bw + 1) the shared
 struct ChunkDesc {
   int g, t0, t1, gt0;      // group, track range, first track of the group
   int pat0, d, W, ebase;   // pattern offset, degree, slots, first sorted edge of the group
-  int nm, R, pad0, pad1;   // multi slots, staged items per track
+  int nm, R, Ts, reg;      // multi slots, staged items per track, E row stride (tracks, padded to 4), regular group
   long long eoff;          // offset of the group's E rows
   long long pad2;
 };
@@ -37,7 +38,7 @@ struct PlanView {
   const int *g_t0;         // [G+1] first track of group g
   const int *g_pat;        // [G+1] offset of group g's pattern (its degree d = g_pat[g+1]-g_pat[g])
   const int *g_W;          // [G]   distinct poses ("slots") touched by group g
-  const long long *g_eoff; // [G+1] offset (floats) of group g's E rows: [T_g][6 W_g]
+  const long long *g_eoff; // [G+1] offset (floats) of group g's E block, entry-major: [6 W_g][Ts_g], Ts = T_g rounded up to 4
   const int *pat_i, *pat_j;    // [sum d] raw source / target pose per pattern position
   const int *pat_li, *pat_lj;  // [sum d] the same as group-local slots
   const int *slot_pose;    // group g's slots (ascending pose ids) at 2*g_pat[g] .. + W_g
@@ -53,6 +54,13 @@ struct PlanView {
   const int *c_t0, *c_grp; // [n_chunks+1], [n_chunks]  edge-pass work units (track ranges)
   const int *u_t0, *u_grp; // [n_units+1],  [n_units]   Schur work units
   const ChunkDesc *cdesc;  // [n_chunks]
+  // lane-per-track edge pass (regular groups): CTA units of <= 32 * kEdge2Warps tracks
+  const int *x_t0, *x_grp; // [n_xchunks+1], [n_xchunks]
+  int n_xchunks;
+  const int *g_reg;        // [G] 1 = regular group (one source slot, no other slot fed twice)
+  int n_irregular;         // groups that need the generic edge pass
+  int dmax_irregular;      // longest track among them
+  const int *patch_track;  // [NM] compact track of a patch or -1
 };
 
 // Per-call view: problem pointers + the layout of the reduced system for this fixedp.

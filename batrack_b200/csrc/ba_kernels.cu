@@ -78,12 +78,12 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
   const int tau = threadIdx.x;
   const ChunkDesc cd = pv.cdesc[blockIdx.x];
   const int g = cd.g, pat0 = cd.pat0, d = cd.d;
-  if (d > NT) return;                                   // long tracks: k_edge_pass_long
-  const int t0 = cd.t0, t1 = cd.t1, gt0 = cd.gt0, W = cd.W, ebase = cd.ebase;
+  if (d > NT || cd.reg) return;                         // long tracks: k_edge_pass_long; regular groups: k_edge_pass_v2
+  const int t0 = cd.t0, t1 = cd.t1, gt0 = cd.gt0, ebase = cd.ebase;
   const int sbase = 2 * pat0;
   const int *slot_pose = pv.slot_pose + sbase;
-  float *Erows = cv.Est + cd.eoff;
-  const int rowlen = 6 * W;
+  float *Erows = cv.Est + cd.eoff;                      // entry-major: [6 W][Ts]
+  const int Ts = cd.Ts;
   const int nm = cd.nm;
   const int *ms_ptr = pv.ms_ptr + sbase + g;
   const int *ms_slot = pv.ms_slot + sbase;
@@ -190,24 +190,20 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
           for (int b = 0; b <= a; ++b) acc[tri(a, b)] += wa0 * et.Jj0[b] + wa1 * et.Jj1[b];  // Bjj, :260
         }
         adjT_apply(pc.R, pc.t, Ej, Ei);                                   // Eik = -A Ejk, ba.py:262
-        float *row = Erows + (size_t)(t - gt0) * rowlen;
+        float *col = Erows + (t - gt0);
         if (rj_rank >= 0) {
 #pragma unroll
           for (int a = 0; a < 6; ++a) stE[a * estride + kappa * R + rj_rank] = Ej[a];
         } else {
-          float2 *dst = reinterpret_cast<float2 *>(row + 6 * lj);         // 24-byte aligned rows: float2 is safe
-          dst[0] = fj ? make_float2(Ej[0], Ej[1]) : make_float2(0.f, 0.f);
-          dst[1] = fj ? make_float2(Ej[2], Ej[3]) : make_float2(0.f, 0.f);
-          dst[2] = fj ? make_float2(Ej[4], Ej[5]) : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int a = 0; a < 6; ++a) col[(size_t)(6 * lj + a) * Ts] = fj ? Ej[a] : 0.0f;
         }
         if (ri_rank >= 0) {
 #pragma unroll
           for (int a = 0; a < 6; ++a) stE[a * estride + kappa * R + ri_rank] = -Ei[a];
         } else {
-          float2 *dst = reinterpret_cast<float2 *>(row + 6 * li);
-          dst[0] = fi ? make_float2(-Ei[0], -Ei[1]) : make_float2(0.f, 0.f);
-          dst[1] = fi ? make_float2(-Ei[2], -Ei[3]) : make_float2(0.f, 0.f);
-          dst[2] = fi ? make_float2(-Ei[4], -Ei[5]) : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int a = 0; a < 6; ++a) col[(size_t)(6 * li + a) * Ts] = fi ? -Ei[a] : 0.0f;
         }
       }
     }
@@ -226,7 +222,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
           const float *src = stE + comp * estride + k2 * R;
           for (int x = ms_ptr[ms]; x < ms_ptr[ms + 1]; ++x) sum += src[x];
         }
-        Erows[(size_t)(t - gt0) * rowlen + 6 * s + comp] = sum;
+        Erows[(size_t)(6 * s + comp) * Ts + (t - gt0)] = sum;
       } else {
         // C and w of the track (ba.py:287,292), then the damped inverse Q and the prior-adjusted w
         // (ba.py:296-311; BA: :184) — fused here so that no separate per-track kernel is needed
@@ -337,6 +333,281 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
   }
 }
 
+// =================================================================================================
+// K1v2  edge pass for REGULAR groups (every SLAM graph: all edges of a track leave its source frame and go to
+//   distinct target frames).  lane <-> track, the warp walks the pattern positions; one CTA = kEdge2Warps warps
+//   = up to 32 * kEdge2Warps consecutive tracks of one group.
+//   * everything per track (C, w, the source slot's E 6-vector, patch, prior) lives in the lane's registers for
+//     the whole walk: no per-track reduction, no barrier inside the walk;
+//   * the (i, j) pair of a position is warp-uniform: Gij / intrinsics come from shared memory as broadcast loads;
+//   * E is entry-major ([6W][Ts]): the 6 stores of a position are 128-byte coalesced rows;
+//   * targets / weights of 4 positions x 32 tracks are staged per warp with cp.async (32-byte segments per
+//     track), two slices in flight, private to the warp (__syncwarp only);
+//   * Bjj / vj of a position are summed over the 32 tracks through a padded shared-memory transpose (27 stores,
+//     8 vector loads per lane) and kept per (warp, position); after the walk the CTA adds the warps' sums in fp64,
+//     maps them to the i side (Bii = A Bjj A^T, Bij = -A Bjj, vi = -A vj, A = Ad(Gij)^T) and issues the fp64
+//     atomics, with Bii / vi pre-summed over the positions (they all hit the same pose block).
+// =================================================================================================
+constexpr int kE2PosBlock = 32;                 // positions per block (constants / per-position sums staged per block)
+constexpr int kE2Slice = 4;                     // positions per cp.async slice
+constexpr int kE2RedStride = 36;                // floats per row of the transpose buffer (conflict-free both ways)
+constexpr int kE2AccStride = 28;
+constexpr int kE2ArrF2 = 32 * (kE2Slice + 1);                       // float2 per staged array: [track][slice + 1]
+constexpr int kE2WarpScratch = kAccComps * kE2RedStride + 2 * 2 * 2 * kE2ArrF2;   // floats: transpose buffer + 2 stages x (targets, weights)
+constexpr int kE2Threads = 32 * kEdge2Warps;
+constexpr int kE2FlushPos = (kEdge2Warps * kE2WarpScratch * 4) / ((kAccComps + 36 + kFlushOuts) * 8) < kE2PosBlock
+                                ? (kEdge2Warps * kE2WarpScratch * 4) / ((kAccComps + 36 + kFlushOuts) * 8) : kE2PosBlock;
+constexpr size_t kEdge2SmemBytes = (size_t)(kEdge2Warps * (kE2WarpScratch + kE2PosBlock * kE2AccStride) +
+                                            kE2PosBlock * kPosFloats + 2 * kE2PosBlock) * sizeof(float);
+static_assert(kE2FlushPos >= 1, "flush scratch too small");
+
+template <bool STRUCT_ONLY>
+__global__ void __launch_bounds__(kE2Threads, 4) k_edge_pass_v2(PlanView pv, CallView cv) {
+  extern __shared__ __align__(16) float dyn_smem[];
+  const int tau = threadIdx.x, lane = tau & 31, warp = tau >> 5;
+  const int xc = blockIdx.x;
+  const int g = pv.x_grp[xc];
+  if (!pv.g_reg[g]) return;                                        // irregular group: generic kernels
+  const int t0 = pv.x_t0[xc], t1 = pv.x_t0[xc + 1];
+  const int gt0 = pv.g_t0[g];
+  const int Ts = (pv.g_t0[g + 1] - gt0 + 3) & ~3;
+  const int pat0 = pv.g_pat[g], d = pv.g_pat[g + 1] - pat0;
+  const int ebase = pv.tptr[gt0];
+  const int *slot_pose = pv.slot_pose + 2 * pat0;
+  float *Eb = cv.Est + pv.g_eoff[g];
+  const int li = pv.pat_li[pat0];                                  // the one source slot of the group
+  const bool fi = pose_free(slot_pose[li], cv);                    // ba.py:33-39 masks
+
+  float *scratch = dyn_smem;                                       // [warps][kE2WarpScratch]; fp64 flush scratch afterwards
+  float *red = scratch + warp * kE2WarpScratch;                    // [27][36]
+  float2 *stage = reinterpret_cast<float2 *>(red + kAccComps * kE2RedStride);   // [2][2][32][5]
+  float *sacc_all = scratch + kEdge2Warps * kE2WarpScratch;        // [warps][32][28]
+  float *sacc = sacc_all + warp * (kE2PosBlock * kE2AccStride);
+  float *sconst = sacc_all + kEdge2Warps * (kE2PosBlock * kE2AccStride);        // [32][20]
+  int *slj = reinterpret_cast<int *>(sconst + kE2PosBlock * kPosFloats);        // [32] target slot of the position
+  int *sfj = slj + kE2PosBlock;                                                 // [32] target pose free?
+
+  const int tw0 = t0 + 32 * warp;                                  // first track of this warp
+  const int t = tw0 + lane;
+  const bool have = t < t1;
+  const bool warp_has = tw0 < t1;
+  float ppx = 0.0f, ppy = 0.0f, ppd = 1.0f, md = 0.0f;
+  if (have) {
+    const size_t kp = (size_t)__ldg(pv.kx + t);
+    const float *pp = cv.patches + 3 * kp;
+    ppx = __ldg(pp); ppy = __ldg(pp + 1); ppd = __ldg(pp + 2);
+    md = cv.monodisp ? __ldg(cv.monodisp + kp) : 0.0f;
+  }
+  float C = 0.0f, w = 0.0f, Eis[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int nW = min(kEdge2Warps, (t1 - t0 + 31) >> 5);            // warps of this CTA that own tracks
+
+  for (int pb = 0; pb < d; pb += kE2PosBlock) {
+    const int np = min(kE2PosBlock, d - pb);
+    __syncthreads();                                               // previous block's flush is done with the scratch
+    if (tau < np) {
+      const int i = pv.pat_i[pat0 + pb + tau], j = pv.pat_j[pat0 + pb + tau];
+      const PairConst c = pair_const(cv.poses + 7 * i, cv.poses + 7 * j, cv.intr + 4 * i, cv.intr + 4 * j);
+      float *o = sconst + tau * kPosFloats;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) o[k] = c.R[k];
+      o[9] = c.t.x; o[10] = c.t.y; o[11] = c.t.z;
+      o[12] = 1.0f / c.fxi; o[13] = 1.0f / c.fyi; o[14] = c.cxi; o[15] = c.cyi;
+      o[16] = c.fxj; o[17] = c.fyj; o[18] = c.cxj; o[19] = c.cyj;
+      slj[tau] = pv.pat_lj[pat0 + pb + tau];
+      sfj[tau] = pose_free(j, cv) ? 1 : 0;
+    }
+    __syncthreads();
+    if (warp_has) {
+      const int nslice = (np + kE2Slice - 1) / kE2Slice;
+      auto issue = [&](int sl) {
+        float2 *bt = stage + (sl & 1) * (2 * kE2ArrF2);
+        const int pp = lane & 3;
+        if (kE2Slice * sl + pp < np) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int tk = (lane >> 2) + 8 * k, tt = tw0 + tk;
+            if (tt < t1) {
+              const int q = ebase + (tt - gt0) * d + pb + kE2Slice * sl + pp;
+              const int e = pv.perm_identity ? q : __ldg(pv.eperm + q);
+              float2 *dt = bt + tk * (kE2Slice + 1) + pp;
+              if (cv.tstride == 2) cp_async8(dt, cv.targets + 2 * (size_t)e);
+              else {
+                const float *tp = cv.targets + (size_t)e * cv.tstride;
+                cp_async4(reinterpret_cast<float *>(dt), tp); cp_async4(reinterpret_cast<float *>(dt) + 1, tp + 1);
+              }
+              cp_async8(dt + kE2ArrF2, cv.weights + 2 * (size_t)e);
+            }
+          }
+        }
+        cp_async_commit();
+      };
+      issue(0);
+      for (int sl = 0; sl < nslice; ++sl) {
+        if (sl + 1 < nslice) { issue(sl + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncwarp();
+        const float2 *bt = stage + (sl & 1) * (2 * kE2ArrF2) + lane * (kE2Slice + 1);
+        const int npp = min(kE2Slice, np - kE2Slice * sl);
+        for (int pp = 0; pp < npp; ++pp) {
+          const int pl = kE2Slice * sl + pp;                       // position within the block (warp-uniform)
+          float2 tg = bt[pp], wg = bt[kE2ArrF2 + pp];
+          if (!have) { tg = make_float2(0.f, 0.f); wg = make_float2(0.f, 0.f); }
+          const float4 *cs = reinterpret_cast<const float4 *>(sconst + pl * kPosFloats);
+          const float4 c0 = cs[0], c1 = cs[1], c2 = cs[2], c3 = cs[3], c4 = cs[4];
+          PairConst pc;
+          pc.R[0] = c0.x; pc.R[1] = c0.y; pc.R[2] = c0.z; pc.R[3] = c0.w;
+          pc.R[4] = c1.x; pc.R[5] = c1.y; pc.R[6] = c1.z; pc.R[7] = c1.w;
+          pc.R[8] = c2.x; pc.t = {c2.y, c2.z, c2.w};
+          pc.cxi = c3.z; pc.cyi = c3.w; pc.fxj = c4.x; pc.fyj = c4.y; pc.cxj = c4.z; pc.cyj = c4.w;
+          pc.fxi = 0.f; pc.fyi = 0.f;                              // unused: the inverses are passed separately
+          EdgeTerms et;
+          edge_terms(pc, c3.x, c3.y, ppx, ppy, ppd, tg.x, tg.y, wg.x, wg.y, cv.bounds, cv.loss, et);
+          const float wz0 = et.w0 * et.Jz0, wz1 = et.w1 * et.Jz1;  // (w Jz)^T, ba.py:255
+          C += wz0 * et.Jz0 + wz1 * et.Jz1;                        // ba.py:287
+          w += wz0 * et.r0 + wz1 * et.r1;                          // ba.py:292
+          if (!STRUCT_ONLY) {
+            float Ej[6], Ei[6];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+              const float wa0 = et.w0 * et.Jj0[a], wa1 = et.w1 * et.Jj1[a];     // (w Jj)^T, ba.py:254
+              Ej[a] = wa0 * et.Jz0 + wa1 * et.Jz1;                              // Ejk, ba.py:263
+              red[(21 + a) * kE2RedStride + lane] = wa0 * et.r0 + wa1 * et.r1;  // vj, ba.py:266
+#pragma unroll
+              for (int b = 0; b <= a; ++b) red[tri(a, b) * kE2RedStride + lane] = wa0 * et.Jj0[b] + wa1 * et.Jj1[b];  // Bjj, :260
+            }
+            adjT_apply(pc.R, pc.t, Ej, Ei);                                     // Eik = -A Ejk, ba.py:262
+#pragma unroll
+            for (int a = 0; a < 6; ++a) Eis[a] -= Ei[a];
+            const int lj = slj[pl];
+            if (lj == li) {                                                     // self edge: its j side feeds the source slot too
+#pragma unroll
+              for (int a = 0; a < 6; ++a) Eis[a] += Ej[a];
+            } else if (have) {
+              const bool fj = sfj[pl] != 0;
+              float *col = Eb + (size_t)(6 * lj) * Ts + (t - gt0);
+#pragma unroll
+              for (int a = 0; a < 6; ++a) col[(size_t)a * Ts] = fj ? Ej[a] : 0.0f;
+            }
+            __syncwarp();
+            if (lane < kAccComps) {                                             // sum of component `lane` over the 32 tracks
+              const float4 *row = reinterpret_cast<const float4 *>(red + lane * kE2RedStride);
+              float4 s4 = row[0];
+#pragma unroll
+              for (int k = 1; k < 8; ++k) { const float4 v = row[k]; s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w; }
+              sacc[pl * kE2AccStride + lane] = (s4.x + s4.y) + (s4.z + s4.w);
+            }
+            __syncwarp();
+          }
+        }
+        __syncwarp();                                              // slice buffer free before it is refilled
+      }
+    }
+    if (!STRUCT_ONLY) {
+      // ---- flush of this block of positions: add the warps' sums (fp64), map to the i side, fp64 atomics ----
+      __syncthreads();
+      constexpr int NT = kE2Threads;
+      double *sumD = reinterpret_cast<double *>(scratch);          // [kE2FlushPos][27]
+      double *ABs = sumD + kE2FlushPos * kAccComps;                // [kE2FlushPos][6][6]  A Bjj
+      double *outD = ABs + kE2FlushPos * 36;                       // [kE2FlushPos][90]
+      const int pi = slot_pose[li];
+      const int ri = 6 * (pi - cv.fixedp);
+      for (int fb = 0; fb < np; fb += kE2FlushPos) {
+        const int nq = min(kE2FlushPos, np - fb);
+        for (int x = tau; x < nq * kAccComps; x += NT) {
+          const int pl = x / kAccComps, k = x - pl * kAccComps;
+          double sv = 0.0;
+          for (int ww = 0; ww < nW; ++ww) sv += (double)sacc_all[(ww * kE2PosBlock + fb + pl) * kE2AccStride + k];
+          sumD[x] = sv;
+        }
+        __syncthreads();
+        for (int x = tau; x < nq * 7; x += NT) {                   // (position, column c of Bjj) and (position, vj)
+          const int pl = x / 7, c = x - pl * 7;
+          const float *cs = sconst + (fb + pl) * kPosFloats;
+          const Vec3 tt{cs[9], cs[10], cs[11]};
+          const double *Sm = sumD + pl * kAccComps;
+          double *o = outD + pl * kFlushOuts;
+          double col[6], res[6];
+          if (c < 6) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) col[a] = Sm[a >= c ? tri(a, c) : tri(c, a)];   // column c of Bjj (= its row c)
+            adjT_apply_d(cs, tt, col, res);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) { ABs[pl * 36 + a * 6 + c] = res[a]; o[42 + 6 * a + c] = -res[a]; }   // Bij = -A Bjj, ba.py:280
+          } else {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) col[a] = Sm[21 + a];
+            adjT_apply_d(cs, tt, col, res);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) { o[78 + a] = col[a]; o[84 + a] = -res[a]; }   // vj ba.py:290; vi = -A vj ba.py:289
+#pragma unroll
+            for (int k = 0; k < 21; ++k) o[k] = Sm[k];                                  // Bjj, ba.py:282
+          }
+        }
+        __syncthreads();
+        for (int x = tau; x < nq * 6; x += NT) {                   // (position, row a): Bii = (A Bjj) A^T, ba.py:279
+          const int pl = x / 6, a = x - pl * 6;
+          const float *cs = sconst + (fb + pl) * kPosFloats;
+          const Vec3 tt{cs[9], cs[10], cs[11]};
+          double rowv[6], res[6];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) rowv[c] = ABs[pl * 36 + a * 6 + c];
+          adjT_apply_d(cs, tt, rowv, res);
+          double *o = outD + pl * kFlushOuts + 21;
+          for (int b2 = 0; b2 <= a; ++b2) o[tri(a, b2)] = res[b2];
+        }
+        __syncthreads();
+        // Bjj, Bij (+ Bji), vj: one atomic per (position, entry); Bii, vi: summed over the positions first
+        for (int x = tau; x < nq * kFlushOuts; x += NT) {
+          const int pl = x / kFlushOuts, o = x - pl * kFlushOuts;
+          if ((o >= 21 && o < 42) || o >= 84) continue;
+          const int pj = pv.pat_j[pat0 + pb + fb + pl];
+          const bool f_j = sfj[fb + pl] != 0;
+          const int rj = 6 * (pj - cv.fixedp);
+          const double val = outD[x];
+          if (o < 21) {
+            if (f_j) red_add(S_at(cv, rj + c_tri_a[o], rj + c_tri_b[o]), val);
+          } else if (o < 78) {
+            if (fi && f_j) {                                 // Bij (rows i, cols j) and Bji = Bij^T, ba.py:280-281
+              const int a = (o - 42) / 6, b = (o - 42) - 6 * a;
+              if (pi > pj) red_add(S_at(cv, ri + a, rj + b), val);
+              else if (pi < pj) red_add(S_at(cv, rj + b, ri + a), val);
+              else if (a >= b) red_add(S_at(cv, ri + a, ri + b), val + outD[pl * kFlushOuts + 42 + 6 * b + a]);
+            }
+          } else {
+            if (f_j) red_add(cv.y + rj + (o - 78), val);
+          }
+        }
+        if (fi && tau < 27) {
+          const int o = tau < 21 ? 21 + tau : 84 + (tau - 21);
+          double sv = 0.0;
+          for (int pl = 0; pl < nq; ++pl) sv += outD[pl * kFlushOuts + o];
+          if (tau < 21) red_add(S_at(cv, ri + c_tri_a[tau], ri + c_tri_b[tau]), sv);
+          else red_add(cv.y + ri + (tau - 21), sv);
+        }
+        __syncthreads();
+      }
+    }
+  }
+
+  if (have) {
+    if (!STRUCT_ONLY) {
+      float *col = Eb + (size_t)(6 * li) * Ts + (t - gt0);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) col[(size_t)a * Ts] = fi ? Eis[a] : 0.0f;
+    }
+    // damped inverse Q and prior-adjusted w (ba.py:296-311; BA: :184)
+    const float lam = cv.lmbda_vec ? cv.lmbda_vec[t] : cv.lmbda;
+    if (cv.monodisp) {
+      const float mk = md > 1e-2f ? 1.0f : 0.0f;
+      C = C + mk * cv.alpha;
+      C = C + lam;
+      w = w - mk * cv.alpha * (ppd - md);
+    } else {
+      C = C + lam;
+    }
+    cv.Qw[t] = make_float2(1.0f / C, w);
+  }
+}
+
 // K1-long: tracks with more than 256 edges (do not occur in BA-Track's graphs, S_slam * steps <= 72;
 // kept so that the operator is total). One thread per edge, float atomics into pre-zeroed E rows / Cw,
 // fp64 atomics into S / y. Slow path.
@@ -346,10 +617,10 @@ __global__ void k_edge_pass_long(PlanView pv, CallView cv) {
   const int g = pv.c_grp[chunk];
   const int pat0 = pv.g_pat[g];
   const int d = pv.g_pat[g + 1] - pat0;
-  if (d <= kEdgeThreads) return;
+  if (d <= kEdgeThreads || pv.g_reg[g]) return;
   const int t0 = pv.c_t0[chunk], t1 = pv.c_t0[chunk + 1];
   const int gt0 = pv.g_t0[g];
-  const int W = pv.g_W[g], rowlen = 6 * W;
+  const int Ts = (pv.g_t0[g + 1] - gt0 + 3) & ~3;
   const int ebase = pv.tptr[gt0];
   const int *slot_pose = pv.slot_pose + 2 * pat0;
   float *Erows = cv.Est + pv.g_eoff[g];
@@ -383,9 +654,9 @@ __global__ void k_edge_pass_long(PlanView pv, CallView cv) {
       for (int b = 0; b <= a; ++b) Bl[tri(a, b)] = (double)(wa0 * et.Jj0[b] + wa1 * et.Jj1[b]);
     }
     adjT_apply(pc.R, pc.t, Ej, Ei);
-    float *row = Erows + (size_t)(t - gt0) * rowlen;
-    if (fj) for (int a = 0; a < 6; ++a) atomicAdd(row + 6 * lj + a, Ej[a]);
-    if (fi) for (int a = 0; a < 6; ++a) atomicAdd(row + 6 * li + a, -Ei[a]);
+    float *col = Erows + (t - gt0);
+    if (fj) for (int a = 0; a < 6; ++a) atomicAdd(col + (size_t)(6 * lj + a) * Ts, Ej[a]);
+    if (fi) for (int a = 0; a < 6; ++a) atomicAdd(col + (size_t)(6 * li + a) * Ts, -Ei[a]);
     const int ri = 6 * (i - cv.fixedp), rj = 6 * (j - cv.fixedp);
     if (fj) for (int a = 0; a < 6; ++a) {
       red_add(cv.y + rj + a, vj[a]);
@@ -422,7 +693,7 @@ __global__ void k_track_q(PlanView pv, CallView cv) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= pv.m) return;
   const int g = pv.t_grp[t];
-  if (pv.g_pat[g + 1] - pv.g_pat[g] <= kEdgeThreads) return;     // the edge pass already wrote (Q, w) for this track
+  if (pv.g_pat[g + 1] - pv.g_pat[g] <= kEdgeThreads || pv.g_reg[g]) return;   // the edge pass already wrote (Q, w) for this track
   const float2 cw = cv.Cw[t];
   const float lam = cv.lmbda_vec ? cv.lmbda_vec[t] : cv.lmbda;
   float C = cw.x, w = cw.y;
@@ -466,13 +737,19 @@ __global__ void __launch_bounds__(kSchurThreads, 2) k_schur(PlanView pv, CallVie
   const int npairs = W * (W + 1) / 2;
   const int nst = (t1 - t0 + tile_tracks - 1) / tile_tracks;
 
-  // stage st <- E rows and (Q, w) of tracks [t0 + st*tile, ...): one contiguous 8-byte-aligned slab each
+  // stage st <- E entries and (Q, w) of tracks [t0 + st*tile, ...). Global E is entry-major ([6W][Ts], coalesced
+  // along tracks); the stage is track-major ([tile][rowlen]) so that a thread reads the 6-vectors of its two slots
+  // with three 8-byte loads each: the copy transposes (4-byte cp.async, consecutive threads = consecutive tracks).
+  const int Ts = (pv.g_t0[g + 1] - gt0 + 3) & ~3;
   auto issue = [&](int st) {
     if (st < nst) {
       const int tt = t0 + st * tile_tracks, nt = min(tile_tracks, t1 - tt);
       float *dst = smem + (size_t)(st % kSchurStages) * stage_floats;
-      const float2 *src = reinterpret_cast<const float2 *>(Erows + (size_t)(tt - gt0) * rowlen);
-      for (int o = tau; o < nt * rowlen / 2; o += NT) cp_async8(reinterpret_cast<float2 *>(dst) + o, src + o);
+      const float *src = Erows + (tt - gt0);
+      for (int o = tau; o < rowlen * tile_tracks; o += NT) {
+        const int r = o / tile_tracks, k = o - r * tile_tracks;
+        if (k < nt) cp_async4(dst + k * rowlen + r, src + (size_t)r * Ts + k);
+      }
       float2 *dq = reinterpret_cast<float2 *>(dst + (size_t)tile_tracks * rowlen);
       for (int o = tau; o < nt; o += NT) cp_async8(dq + o, cv.Qw + tt + o);
     }
@@ -786,17 +1063,11 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_dense(CallView cv, int 
 }
 
 // =================================================================================================
-// K4  back-substitution dZ = Q (w - E^T dX) (ba.py:328 / :317), disparity retraction + clamp
-//     (ba.py:42-44,332-334). One warp per track.
+// K4  back-substitution dZ = Q (w - E^T dX) (ba.py:328 / :317), disparity retraction + clamp of EVERY patch
+//     (ba.py:42-44,332-334) and the fresh patches tensor, in one pass: one thread per patch. E is entry-major, so
+//     consecutive threads (consecutive tracks of a group) read consecutive floats; the pose of a slot and its dX
+//     are uniform across the threads of a group.
 // =================================================================================================
-__global__ void k_patches_copy_clamp(const float *__restrict__ in, float *__restrict__ out, int NM) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= NM) return;
-  out[3 * (size_t)k] = in[3 * (size_t)k];
-  out[3 * (size_t)k + 1] = in[3 * (size_t)k + 1];
-  out[3 * (size_t)k + 2] = fminf(fmaxf(in[3 * (size_t)k + 2], 1e-3f), 10.0f);   // clamp hits every patch, ba.py:333
-}
-
 __device__ __forceinline__ void pose_retr_one(const CallView &cv, int i) {
   float a[6] = {0, 0, 0, 0, 0, 0};
   if (pose_free(i, cv)) {
@@ -810,37 +1081,44 @@ __device__ __forceinline__ void pose_retr_one(const CallView &cv, int i) {
   pose_store(r, cv.poses_out + 7 * (size_t)i);
 }
 
-// blocks [0, nb_back): one warp per track; blocks beyond: pose retraction T <- Exp(dx) T for every pose of the
+// blocks [0, nb_back): one thread per patch; blocks beyond: pose retraction T <- Exp(dx) T for every pose of the
 // buffer, dx = 0 outside the window (ba.py:47-49,336-337; lietorch/groups.py:153-156), when retr_n > 0
-__global__ void k_backsub(PlanView pv, CallView cv, int use_dx, int nb_back, int retr_n) {
+__global__ void __launch_bounds__(256) k_backsub(PlanView pv, CallView cv, int use_dx, int nb_back, int retr_n) {
   if ((int)blockIdx.x >= nb_back) {
     const int i = ((int)blockIdx.x - nb_back) * blockDim.x + threadIdx.x;
     if (i < retr_n) pose_retr_one(cv, i);
     return;
   }
-  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (t >= pv.m) return;
-  const float2 qw = cv.Qw[t];
-  double dot = 0.0;
-  if (use_dx) {
-    const int g = pv.t_grp[t];
-    const int W = pv.g_W[g], rowlen = 6 * W;
-    const int *slot_pose = pv.slot_pose + 2 * pv.g_pat[g];
-    const float *row = cv.Est + pv.g_eoff[g] + (size_t)(t - pv.g_t0[g]) * rowlen;
-    for (int r = lane; r < rowlen; r += 32) {
-      const int s = r / 6;
-      const int pose = slot_pose[s];
-      if (pose_free(pose, cv)) dot += (double)row[r] * cv.dX[6 * (pose - cv.fixedp) + (r - 6 * s)];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= pv.NM) return;
+  const float px = cv.patches[3 * (size_t)k], py = cv.patches[3 * (size_t)k + 1];
+  float dsp = cv.patches[3 * (size_t)k + 2];
+  const int t = pv.patch_track[k];
+  if (t >= 0) {
+    const float2 qw = cv.Qw[t];
+    double dot = 0.0;
+    if (use_dx) {
+      const int g = pv.t_grp[t];
+      const int W = pv.g_W[g], gt0 = pv.g_t0[g];
+      const int Ts = (pv.g_t0[g + 1] - gt0 + 3) & ~3;
+      const int *slot_pose = pv.slot_pose + 2 * pv.g_pat[g];
+      const float *col = cv.Est + pv.g_eoff[g] + (t - gt0);
+      for (int sl = 0; sl < W; ++sl) {
+        const int pose = slot_pose[sl];
+        if (!pose_free(pose, cv)) continue;
+        const double *dx = cv.dX + 6 * (pose - cv.fixedp);
+        const float *e = col + (size_t)(6 * sl) * Ts;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dot += (double)e[(size_t)c * Ts] * dx[c];
+      }
     }
-    for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  }
-  if (lane == 0) {
     const float dz = (float)((double)qw.x * ((double)qw.y - dot));
     cv.dZ[t] = dz;
-    const size_t k = (size_t)pv.kx[t];
-    cv.patches_out[3 * k + 2] = fminf(fmaxf(cv.patches[3 * k + 2] + dz, 1e-3f), 10.0f);
+    dsp += dz;
   }
+  cv.patches_out[3 * (size_t)k] = px;
+  cv.patches_out[3 * (size_t)k + 1] = py;
+  cv.patches_out[3 * (size_t)k + 2] = fminf(fmaxf(dsp, 1e-3f), 10.0f);          // clamp hits every patch, ba.py:333
 }
 
 // ---- debug: expand the lower (band) storage to a dense symmetric matrix, cast fp64 -> fp32 --------
@@ -896,20 +1174,31 @@ extern "C" int ba_assemble(BaPlan *pl, const BaProblem *pb, void *stream_) {
     BA_CUDA(cudaFuncSetAttribute(k_edge_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
     edge_attr_set = true;
   }
-  const bool has_long = pv.dmax > kEdgeThreads;
+  static bool edge2_attr_set = false;
+  if (!edge2_attr_set) {
+    BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdge2SmemBytes));
+    BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdge2SmemBytes));
+    edge2_attr_set = true;
+  }
+  // regular groups (every SLAM graph): lane-per-track kernel; irregular groups: the generic kernels (each kernel
+  // returns at once on the groups of the other kind)
+  const bool any_regular = pv.n_irregular < pv.G, any_irregular = pv.n_irregular > 0;
+  const bool has_long = any_irregular && pv.dmax_irregular > kEdgeThreads;
   if (has_long) {   // the slow path accumulates with atomics: its targets start from zero
     BA_CUDA(cudaMemsetAsync(cv.Cw, 0, (size_t)pv.m * sizeof(float2), s));
     if (!so) BA_CUDA(cudaMemsetAsync(cv.Est, 0, (size_t)pl->est_floats * sizeof(float), s));
   }
   if (so) {
     BA_MARK(pl, BA_STAGE_EDGE, s);
-    k_edge_pass<true><<<pv.n_chunks, kEdgeThreads, kEdgeSmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK();
+    if (any_regular) { k_edge_pass_v2<true><<<pv.n_xchunks, kE2Threads, kEdge2SmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
+    if (any_irregular) { k_edge_pass<true><<<pv.n_chunks, kEdgeThreads, kEdgeSmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
     if (has_long) { k_edge_pass_long<true><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
   } else {
     BA_MARK(pl, BA_STAGE_ZERO, s);
     BA_CUDA(cudaMemsetAsync(cv.S, 0, (size_t)((cv.y - cv.S) + cv.M) * sizeof(double), s));
     BA_MARK(pl, BA_STAGE_EDGE, s);
-    k_edge_pass<false><<<pv.n_chunks, kEdgeThreads, kEdgeSmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK();
+    if (any_regular) { k_edge_pass_v2<false><<<pv.n_xchunks, kE2Threads, kEdge2SmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
+    if (any_irregular) { k_edge_pass<false><<<pv.n_chunks, kEdgeThreads, kEdgeSmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
     if (has_long) { k_edge_pass_long<false><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
   }
   BA_MARK(pl, BA_STAGE_TRACKQ, s);
@@ -976,9 +1265,8 @@ extern "C" int ba_solve_update(BaPlan *pl, const BaProblem *pb, void *stream_) {
     }
   }
   BA_MARK(pl, BA_STAGE_BACKSUB, s);
-  k_patches_copy_clamp<<<(pv.NM + 255) / 256, 256, 0, s>>>(pb->patches, pb->patches_out, pv.NM); BA_LAUNCH_CHECK();
   {
-    const int nb_back = (int)(((int64_t)pv.m * 32 + 255) / 256), nb_retr = so ? 0 : (pv.N + 255) / 256;
+    const int nb_back = (pv.NM + 255) / 256, nb_retr = so ? 0 : (pv.N + 255) / 256;
     k_backsub<<<nb_back + nb_retr, 256, 0, s>>>(pv, cv, so ? 0 : 1, nb_back, so ? 0 : pv.N); BA_LAUNCH_CHECK();
   }
   BA_MARK(pl, BA_STAGE_RETR, s);

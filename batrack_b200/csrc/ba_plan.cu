@@ -38,7 +38,7 @@ int set_cuda_error(cudaError_t e, const char *what) {
 }
 
 // meta block written by the prep kernels
-enum { META_ERR = 0, META_MAXPOSE, META_NOTIDENT, META_DMAX, META_WMAX, META_SPAN, META_COUNT = 8 };
+enum { META_ERR = 0, META_MAXPOSE, META_NOTIDENT, META_DMAX, META_WMAX, META_SPAN, META_NIRREG, META_DMAX_IRREG, META_COUNT = 8 };
 
 __global__ void k_prep_keys(const int64_t *__restrict__ ii, const int64_t *__restrict__ jj,
                             const int64_t *__restrict__ kk, int64_t E, int N, int NM,
@@ -116,7 +116,7 @@ __global__ void k_chunk_flags(const int *__restrict__ t_grp, const int *__restri
   const int g = t_grp[t];
   const int T = g_t0[g + 1] - g_t0[g];
   const int pieces = (T + tc - 1) / tc;
-  const int len = (T + pieces - 1) / pieces;
+  const int len = ((T + pieces - 1) / pieces + 3) & ~3;          // multiple of 4: 16-byte aligned starts in the E rows
   cflag[t] = ((t - g_t0[g]) % len == 0) ? 1 : 0;
 }
 __global__ void k_fill_chunks(const int *__restrict__ cflag, const int *__restrict__ cinc,
@@ -144,7 +144,8 @@ __global__ void k_group_slots(const int *__restrict__ g_t0, const int *__restric
                               int *__restrict__ slot_ptr, int *__restrict__ slot_items,
                               int *__restrict__ g_nm, int *__restrict__ ms_ptr, int *__restrict__ ms_slot,
                               int *__restrict__ pat_ri, int *__restrict__ pat_rj,
-                              int *__restrict__ g_W, long long *__restrict__ g_esz, int *__restrict__ meta) {
+                              int *__restrict__ g_W, long long *__restrict__ g_esz, int *__restrict__ g_reg,
+                              int *__restrict__ meta) {
   extern __shared__ unsigned sm[];
   const int g = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int nwords = (N + 31) >> 5;
@@ -225,7 +226,16 @@ __global__ void k_group_slots(const int *__restrict__ g_t0, const int *__restric
     mp[nm] = R;
     g_nm[g] = nm;
     g_W[g] = W;
-    g_esz[g] = (long long)T * 6 * W;
+    // E rows are stored entry-major ("SoA"): [6 W][Ts] floats, Ts = T rounded up to 4 (16-byte rows)
+    g_esz[g] = (long long)((T + 3) & ~3) * 6 * W;
+    // "regular" group (every SLAM graph: one source frame per track, distinct target frames): all positions share
+    // the source slot and no other slot is fed twice -> the lane-per-track edge pass (k_edge_pass_v2) applies
+    bool reg = true;
+    const int s0 = pat_li[pat0];
+    for (int p = 0; p < d; ++p) reg = reg && pat_li[pat0 + p] == s0;
+    for (int s = 0; s < W; ++s) reg = reg && (s == s0 || sp[s + 1] - sp[s] < 2);
+    g_reg[g] = reg ? 1 : 0;
+    if (!reg) { atomicAdd(&meta[META_NIRREG], 1); atomicMax(&meta[META_DMAX_IRREG], d); }
     atomicMax(&meta[META_WMAX], W);
     int lo = slot_pose[sbase], hi = slot_pose[sbase + W - 1];
     atomicMax(&meta[META_SPAN], hi - lo);
@@ -234,13 +244,19 @@ __global__ void k_group_slots(const int *__restrict__ g_t0, const int *__restric
 
 __global__ void k_zero_last(long long *p, int idx) { p[idx] = 0; }
 
+// inverse of kx: compact track of a patch, -1 for patches without edges (back-substitution runs per patch)
+__global__ void k_patch_track(const int *__restrict__ kx, int m, int *__restrict__ patch_track) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < m) patch_track[kx[t]] = t;
+}
+
 __global__ void k_chunk_desc(PlanView v, ChunkDesc *out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= v.n_chunks) return;
   ChunkDesc d;
   d.g = v.c_grp[c]; d.t0 = v.c_t0[c]; d.t1 = v.c_t0[c + 1]; d.gt0 = v.g_t0[d.g];
   d.pat0 = v.g_pat[d.g]; d.d = v.g_pat[d.g + 1] - d.pat0; d.W = v.g_W[d.g]; d.ebase = v.tptr[d.gt0];
-  d.nm = v.g_nm[d.g]; d.R = v.ms_ptr[2 * d.pat0 + d.g + d.nm]; d.pad0 = d.pad1 = 0;
+  d.nm = v.g_nm[d.g]; d.R = v.ms_ptr[2 * d.pat0 + d.g + d.nm]; d.Ts = (v.g_t0[d.g + 1] - d.gt0 + 3) & ~3; d.reg = v.g_reg[d.g];
   d.eoff = v.g_eoff[d.g]; d.pad2 = 0;
   out[c] = d;
 }
@@ -396,10 +412,10 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     PL_CUDA(cudaMemcpyAsync(&G, ginc + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
     PL_CUDA(cudaStreamSynchronize(s));
 
-    int *g_t0, *g_pat, *g_W, *g_d;
+    int *g_t0, *g_pat, *g_W, *g_d, *g_reg;
     long long *g_eoff, *g_esz;
     PL_CUDA(own(pl, &g_t0, G + 1)); PL_CUDA(own(pl, &g_pat, G + 1)); PL_CUDA(own(pl, &g_W, G));
-    PL_CUDA(own(pl, &g_eoff, G + 1));
+    PL_CUDA(own(pl, &g_eoff, G + 1)); PL_CUDA(own(pl, &g_reg, G));
     PL_CUDA(sc.get(&g_d, G + 1)); PL_CUDA(sc.get(&g_esz, G + 1));
     k_fill_groups<<<cdiv(m, TB), TB, 0, s>>>(gflag, ginc, m, g_t0, t_grp); PL_LAUNCH();
     k_group_degree<<<cdiv(G + 1, TB), TB, 0, s>>>(g_t0, tptr, G, g_d); PL_LAUNCH();
@@ -415,10 +431,13 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     if (const char *e = getenv("BA_SCHUR_TU")) tu = std::max(1, atoi(e));
     int *cflag, *cinc;
     PL_CUDA(sc.get(&cflag, m)); PL_CUDA(sc.get(&cinc, m));
-    int counts[2] = {0, 0};
-    int *unit_t0[2], *unit_grp[2];
-    for (int pass = 0; pass < 2; ++pass) {
-      k_chunk_flags<<<cdiv(m, TB), TB, 0, s>>>(t_grp, g_t0, m, pass == 0 ? tc : tu, cflag); PL_LAUNCH();
+    // lane-per-track edge pass: one CTA of kEdge2Warps warps per <= 32 * kEdge2Warps tracks of a group
+    int tx = 32 * kEdge2Warps;
+    if (const char *e = getenv("BA_EDGE2_TX")) tx = std::max(32, std::min(32 * kEdge2Warps, atoi(e)));
+    int counts[3] = {0, 0, 0};
+    int *unit_t0[3], *unit_grp[3];
+    for (int pass = 0; pass < 3; ++pass) {
+      k_chunk_flags<<<cdiv(m, TB), TB, 0, s>>>(t_grp, g_t0, m, pass == 0 ? tc : (pass == 1 ? tu : tx), cflag); PL_LAUNCH();
       PL_CUDA(inclusive_sum(sc, cflag, cinc, m, s));
       PL_CUDA(cudaMemcpyAsync(&counts[pass], cinc + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
       PL_CUDA(cudaStreamSynchronize(s));
@@ -441,7 +460,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
       int nwords = (N + 31) / 32;
       size_t smem = (size_t)(2 * nwords + 1) * sizeof(int);
       k_group_slots<<<G, 128, smem, s>>>(g_t0, g_pat, tptr, sij, N, pat_i, pat_j, pat_li, pat_lj, slot_pose,
-                                         slot_ptr, slot_items, g_nm, ms_ptr, ms_slot, pat_ri, pat_rj, g_W, g_esz, meta); PL_LAUNCH();
+                                         slot_ptr, slot_items, g_nm, ms_ptr, ms_slot, pat_ri, pat_rj, g_W, g_esz, g_reg, meta); PL_LAUNCH();
     }
     k_zero_last<<<1, 1, 0, s>>>(g_esz, G); PL_LAUNCH();
     PL_CUDA(exclusive_sum(sc, g_esz, g_eoff, G + 1, s));
@@ -458,6 +477,15 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     v.slot_pose = slot_pose; v.slot_ptr = slot_ptr; v.slot_items = slot_items;
     v.g_nm = g_nm; v.ms_ptr = ms_ptr; v.ms_slot = ms_slot; v.pat_ri = pat_ri; v.pat_rj = pat_rj; v.dmax = hmeta[META_DMAX];
     v.c_t0 = unit_t0[0]; v.c_grp = unit_grp[0]; v.u_t0 = unit_t0[1]; v.u_grp = unit_grp[1];
+    v.x_t0 = unit_t0[2]; v.x_grp = unit_grp[2]; v.n_xchunks = counts[2];
+    v.g_reg = g_reg; v.n_irregular = hmeta[META_NIRREG]; v.dmax_irregular = hmeta[META_DMAX_IRREG];
+    {
+      int *ptk;
+      PL_CUDA(own(pl, &ptk, NM));
+      PL_CUDA(cudaMemsetAsync(ptk, 0xff, (size_t)NM * sizeof(int), s));
+      k_patch_track<<<cdiv(m, TB), TB, 0, s>>>(kx, m, ptk); PL_LAUNCH();
+      v.patch_track = ptk;
+    }
 
     {
       ChunkDesc *cd;
@@ -474,6 +502,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     pl->bwb_layout = in.block_bandwidth;
 
     PL_CUDA(own(pl, &pl->Est, (size_t)esize + 8));
+    PL_CUDA(cudaMemsetAsync(pl->Est, 0, ((size_t)esize + 8) * sizeof(float), s));   // row padding stays zero (finite) for ever
     pl->est_floats = esize;
     PL_CUDA(own(pl, &pl->Cw, m)); PL_CUDA(own(pl, &pl->Qw, m)); PL_CUDA(own(pl, &pl->dZ, m));
     PL_CUDA(own(pl, &pl->status, 4));
