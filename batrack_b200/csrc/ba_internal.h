@@ -11,7 +11,8 @@
 namespace ba {
 
 constexpr int kEdgeThreads = 256;     // CTA size of the generic edge pass (irregular groups)
-constexpr int kEdge2Warps = 4;        // warps per CTA of the lane-per-track edge pass (32 tracks per warp)
+constexpr int kMaxSlotRun = 24;       // most positions of a track that may feed one E slot in the lane-per-track edge pass
+constexpr int kEdge2Warps = 8;        // warps per CTA of the lane-per-track edge pass: KT track slices x KP position splits
 constexpr int kSchurThreads = 256;    // CTA size of the per-track Schur kernel
 constexpr int kSolveThreads = 1024;   // CTA size of the window Cholesky
 constexpr int kMaxWindow = 150;       // largest band window (bw + 1) the shared-memory solver holds (fp64)
@@ -54,10 +55,12 @@ struct PlanView {
   const int *c_t0, *c_grp; // [n_chunks+1], [n_chunks]  edge-pass work units (track ranges)
   const int *u_t0, *u_grp; // [n_units+1],  [n_units]   Schur work units
   const ChunkDesc *cdesc;  // [n_chunks]
-  // lane-per-track edge pass (regular groups): CTA units of <= 32 * kEdge2Warps tracks
+  // lane-per-track edge pass (regular groups): CTA units of <= 32 * (kEdge2Warps / e2_kp) tracks
+  int e2_kp;               // position splits per track slice (1, 2, 4 or 8)
   const int *x_t0, *x_grp; // [n_xchunks+1], [n_xchunks]
   int n_xchunks;
-  const int *g_reg;        // [G] 1 = regular group (one source slot, no other slot fed twice)
+  const int *g_reg;        // [G] 1 = regular group (one source slot; no target slot fed more than kMaxSlotRun times)
+  const int *pat_ps;       // [sum d] positions of a group ordered by (target slot, position)
   int n_irregular;         // groups that need the generic edge pass
   int dmax_irregular;      // longest track among them
   const int *patch_track;  // [NM] compact track of a patch or -1

@@ -335,21 +335,23 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
 
 // =================================================================================================
 // K1v2  edge pass for REGULAR groups (every SLAM graph: all edges of a track leave its source frame and go to
-//   distinct target frames).  lane <-> track, the warp walks the pattern positions; one CTA = kEdge2Warps warps
-//   = up to 32 * kEdge2Warps consecutive tracks of one group.
-//   * everything per track (C, w, the source slot's E 6-vector, patch, prior) lives in the lane's registers for
-//     the whole walk: no per-track reduction, no barrier inside the walk;
+//   distinct target frames).  lane <-> track, a warp walks pattern positions.  One CTA = 8 warps arranged as
+//   KT track slices (32 consecutive tracks each) x KP position splits (KT * KP = 8, KP chosen by the plan from the
+//   track length so that a warp walks ~8-10 positions and the machine sees enough warps on small graphs too).
+//   * per track quantities (C, w, the source slot's E 6-vector, patch, prior) live in the lane's registers for
+//     the whole walk: no per-track reduction and no CTA barrier inside the walk; the KP partial sums of a track
+//     meet once, in shared memory, in fixed order;
 //   * the (i, j) pair of a position is warp-uniform: Gij / intrinsics come from shared memory as broadcast loads;
 //   * E is entry-major ([6W][Ts]): the 6 stores of a position are 128-byte coalesced rows;
-//   * targets / weights of 4 positions x 32 tracks are staged per warp with cp.async (32-byte segments per
-//     track), two slices in flight, private to the warp (__syncwarp only);
+//   * targets / weights of 2 positions x 32 tracks are staged per warp with cp.async, two slices in flight,
+//     private to the warp (__syncwarp only);
 //   * Bjj / vj of a position are summed over the 32 tracks through a padded shared-memory transpose (27 stores,
-//     8 vector loads per lane) and kept per (warp, position); after the walk the CTA adds the warps' sums in fp64,
-//     maps them to the i side (Bii = A Bjj A^T, Bij = -A Bjj, vi = -A vj, A = Ad(Gij)^T) and issues the fp64
-//     atomics, with Bii / vi pre-summed over the positions (they all hit the same pose block).
+//     8 vector loads per lane) and kept per (track slice, position); after the walk the CTA adds the slices' sums
+//     in fp64, maps them to the i side (Bii = A Bjj A^T, Bij = -A Bjj, vi = -A vj, A = Ad(Gij)^T) and issues the
+//     fp64 atomics, with Bii / vi pre-summed over the positions (they all hit the same pose block).
 // =================================================================================================
 constexpr int kE2PosBlock = 32;                 // positions per block (constants / per-position sums staged per block)
-constexpr int kE2Slice = 4;                     // positions per cp.async slice
+constexpr int kE2Slice = 2;                     // positions per cp.async slice
 constexpr int kE2RedStride = 36;                // floats per row of the transpose buffer (conflict-free both ways)
 constexpr int kE2AccStride = 28;
 constexpr int kE2ArrF2 = 32 * (kE2Slice + 1);                       // float2 per staged array: [track][slice + 1]
@@ -357,17 +359,23 @@ constexpr int kE2WarpScratch = kAccComps * kE2RedStride + 2 * 2 * 2 * kE2ArrF2; 
 constexpr int kE2Threads = 32 * kEdge2Warps;
 constexpr int kE2FlushPos = (kEdge2Warps * kE2WarpScratch * 4) / ((kAccComps + 36 + kFlushOuts) * 8) < kE2PosBlock
                                 ? (kEdge2Warps * kE2WarpScratch * 4) / ((kAccComps + 36 + kFlushOuts) * 8) : kE2PosBlock;
-constexpr size_t kEdge2SmemBytes = (size_t)(kEdge2Warps * (kE2WarpScratch + kE2PosBlock * kE2AccStride) +
-                                            kE2PosBlock * kPosFloats + 2 * kE2PosBlock) * sizeof(float);
+// dynamic shared memory: per warp scratch, per track slice (KT = kEdge2Warps / KP) the per-position sums, constants
+static size_t edge2_smem_bytes(int kp) {
+  return (size_t)(kEdge2Warps * kE2WarpScratch + (kEdge2Warps / kp) * kE2PosBlock * kE2AccStride +
+                  kE2PosBlock * kPosFloats + 5 * kE2PosBlock + 8) * sizeof(float);
+}
 static_assert(kE2FlushPos >= 1, "flush scratch too small");
+static_assert(kEdge2Warps * 8 * 32 <= kEdge2Warps * kE2WarpScratch, "per-track partials alias the scratch");
 
 template <bool STRUCT_ONLY>
-__global__ void __launch_bounds__(kE2Threads, 4) k_edge_pass_v2(PlanView pv, CallView cv) {
+__global__ void __launch_bounds__(kE2Threads, 3) k_edge_pass_v2(PlanView pv, CallView cv) {
   extern __shared__ __align__(16) float dyn_smem[];
   const int tau = threadIdx.x, lane = tau & 31, warp = tau >> 5;
   const int xc = blockIdx.x;
   const int g = pv.x_grp[xc];
   if (!pv.g_reg[g]) return;                                        // irregular group: generic kernels
+  const int KP = pv.e2_kp;                                         // position splits; KT = kEdge2Warps / KP track slices
+  const int ks = warp / KP, sp = warp - ks * KP;
   const int t0 = pv.x_t0[xc], t1 = pv.x_t0[xc + 1];
   const int gt0 = pv.g_t0[g];
   const int Ts = (pv.g_t0[g + 1] - gt0 + 3) & ~3;
@@ -380,32 +388,55 @@ __global__ void __launch_bounds__(kE2Threads, 4) k_edge_pass_v2(PlanView pv, Cal
 
   float *scratch = dyn_smem;                                       // [warps][kE2WarpScratch]; fp64 flush scratch afterwards
   float *red = scratch + warp * kE2WarpScratch;                    // [27][36]
-  float2 *stage = reinterpret_cast<float2 *>(red + kAccComps * kE2RedStride);   // [2][2][32][5]
-  float *sacc_all = scratch + kEdge2Warps * kE2WarpScratch;        // [warps][32][28]
-  float *sacc = sacc_all + warp * (kE2PosBlock * kE2AccStride);
-  float *sconst = sacc_all + kEdge2Warps * (kE2PosBlock * kE2AccStride);        // [32][20]
-  int *slj = reinterpret_cast<int *>(sconst + kE2PosBlock * kPosFloats);        // [32] target slot of the position
-  int *sfj = slj + kE2PosBlock;                                                 // [32] target pose free?
+  float2 *stage = reinterpret_cast<float2 *>(red + kAccComps * kE2RedStride);   // [2][2][32][slice + 1]
+  float *sacc_all = scratch + kEdge2Warps * kE2WarpScratch;        // [track slice][32][28]
+  float *sacc = sacc_all + ks * (kE2PosBlock * kE2AccStride);
+  float *sconst = sacc_all + (kEdge2Warps / KP) * (kE2PosBlock * kE2AccStride); // [32][20]
+  int *slj = reinterpret_cast<int *>(sconst + kE2PosBlock * kPosFloats);        // [32 + 1] target slot of the position (+ look-ahead)
+  int *sfj = slj + kE2PosBlock + 1;                                             // [32] target pose free?
+  int *spp = sfj + kE2PosBlock;                                                 // [32] pattern position (edge offset in the track)
+  int *spj = spp + kE2PosBlock;                                                 // [32] target pose
+  int *hlist = spj + kE2PosBlock;                                               // [32] block positions that start a slot run
+  int *s_ctl = hlist + kE2PosBlock;                                             // [0] positions in this block, [1] run heads
 
-  const int tw0 = t0 + 32 * warp;                                  // first track of this warp
+  const int tw0 = t0 + 32 * ks;                                    // first track of this warp's slice
   const int t = tw0 + lane;
   const bool have = t < t1;
   const bool warp_has = tw0 < t1;
-  float ppx = 0.0f, ppy = 0.0f, ppd = 1.0f, md = 0.0f;
+  float ppx = 0.0f, ppy = 0.0f, ppd = 1.0f;
   if (have) {
-    const size_t kp = (size_t)__ldg(pv.kx + t);
-    const float *pp = cv.patches + 3 * kp;
+    const float *pp = cv.patches + 3 * (size_t)__ldg(pv.kx + t);
     ppx = __ldg(pp); ppy = __ldg(pp + 1); ppd = __ldg(pp + 2);
-    md = cv.monodisp ? __ldg(cv.monodisp + kp) : 0.0f;
   }
-  float C = 0.0f, w = 0.0f, Eis[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const int nW = min(kEdge2Warps, (t1 - t0 + 31) >> 5);            // warps of this CTA that own tracks
+  float C = 0.0f, w = 0.0f, Eis[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Ejs[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int hd = 0;
+  const int nS = min(kEdge2Warps / KP, (t1 - t0 + 31) >> 5);       // track slices of this CTA that own tracks
 
-  for (int pb = 0; pb < d; pb += kE2PosBlock) {
-    const int np = min(kE2PosBlock, d - pb);
+  // The walk follows pat_ps: positions ordered by target slot, so that the positions feeding one E slot (a SLAM
+  // graph observes a (patch, frame) pair several times) are consecutive; blocks of <= 32 positions and the KP
+  // splits are cut at slot boundaries, and a lane adds the 6-vectors of a run in registers before the one store.
+  const int *ps = pv.pat_ps + pat0;
+  for (int pb = 0; pb < d;) {
     __syncthreads();                                               // previous block's flush is done with the scratch
+    if (tau <= kE2PosBlock) {
+      int lj = -1;
+      if (pb + tau < d) { const int p = ps[pb + tau]; lj = pv.pat_lj[pat0 + p]; if (tau < kE2PosBlock) spp[tau] = p; }
+      slj[tau] = lj;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int e = min(kE2PosBlock, d - pb);
+      if (pb + e < d) { while (e > 1 && slj[e] == slj[e - 1]) --e; }           // runs are <= kMaxSlotRun < 32 long
+      const bool head = lane < e && (lane == 0 || slj[lane] != slj[lane - 1]);
+      const unsigned hm = __ballot_sync(0xffffffffu, head);
+      if (head) hlist[__popc(hm & ((1u << lane) - 1u))] = lane;
+      if (lane == 0) { s_ctl[0] = e; s_ctl[1] = __popc(hm); }
+    }
+    __syncthreads();
+    const int np = s_ctl[0], nh = s_ctl[1];
     if (tau < np) {
-      const int i = pv.pat_i[pat0 + pb + tau], j = pv.pat_j[pat0 + pb + tau];
+      const int p = spp[tau];
+      const int i = pv.pat_i[pat0 + p], j = pv.pat_j[pat0 + p];
       const PairConst c = pair_const(cv.poses + 7 * i, cv.poses + 7 * j, cv.intr + 4 * i, cv.intr + 4 * j);
       float *o = sconst + tau * kPosFloats;
 #pragma unroll
@@ -413,21 +444,27 @@ __global__ void __launch_bounds__(kE2Threads, 4) k_edge_pass_v2(PlanView pv, Cal
       o[9] = c.t.x; o[10] = c.t.y; o[11] = c.t.z;
       o[12] = 1.0f / c.fxi; o[13] = 1.0f / c.fyi; o[14] = c.cxi; o[15] = c.cyi;
       o[16] = c.fxj; o[17] = c.fyj; o[18] = c.cxj; o[19] = c.cyj;
-      slj[tau] = pv.pat_lj[pat0 + pb + tau];
+      spj[tau] = j;
       sfj[tau] = pose_free(j, cv) ? 1 : 0;
     }
     __syncthreads();
-    if (warp_has) {
-      const int nslice = (np + kE2Slice - 1) / kE2Slice;
+    // this warp's positions of the block: [pw0, pw1), cut at slot boundaries
+    const int per = (np + KP - 1) / KP;
+    int pw0 = min(np, sp * per), pw1 = min(np, (sp + 1) * per);
+    while (pw0 > 0 && pw0 < np && slj[pw0] == slj[pw0 - 1]) ++pw0;
+    while (pw1 > 0 && pw1 < np && slj[pw1] == slj[pw1 - 1]) ++pw1;
+    if (warp_has && pw0 < pw1) {
+      const int nslice = (pw1 - pw0 + kE2Slice - 1) / kE2Slice;
       auto issue = [&](int sl) {
         float2 *bt = stage + (sl & 1) * (2 * kE2ArrF2);
-        const int pp = lane & 3;
-        if (kE2Slice * sl + pp < np) {
+        const int pp = lane & (kE2Slice - 1);
+        const int pl = pw0 + kE2Slice * sl + pp;
+        if (pl < pw1) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int tk = (lane >> 2) + 8 * k, tt = tw0 + tk;
+          for (int k = 0; k < kE2Slice; ++k) {
+            const int tk = lane / kE2Slice + (32 / kE2Slice) * k, tt = tw0 + tk;
             if (tt < t1) {
-              const int q = ebase + (tt - gt0) * d + pb + kE2Slice * sl + pp;
+              const int q = ebase + (tt - gt0) * d + spp[pl];
               const int e = pv.perm_identity ? q : __ldg(pv.eperm + q);
               float2 *dt = bt + tk * (kE2Slice + 1) + pp;
               if (cv.tstride == 2) cp_async8(dt, cv.targets + 2 * (size_t)e);
@@ -446,9 +483,9 @@ __global__ void __launch_bounds__(kE2Threads, 4) k_edge_pass_v2(PlanView pv, Cal
         if (sl + 1 < nslice) { issue(sl + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncwarp();
         const float2 *bt = stage + (sl & 1) * (2 * kE2ArrF2) + lane * (kE2Slice + 1);
-        const int npp = min(kE2Slice, np - kE2Slice * sl);
+        const int npp = min(kE2Slice, pw1 - pw0 - kE2Slice * sl);
         for (int pp = 0; pp < npp; ++pp) {
-          const int pl = kE2Slice * sl + pp;                       // position within the block (warp-uniform)
+          const int pl = pw0 + kE2Slice * sl + pp;                 // position within the block (warp-uniform)
           float2 tg = bt[pp], wg = bt[kE2ArrF2 + pp];
           if (!have) { tg = make_float2(0.f, 0.f); wg = make_float2(0.f, 0.f); }
           const float4 *cs = reinterpret_cast<const float4 *>(sconst + pl * kPosFloats);
@@ -478,22 +515,34 @@ __global__ void __launch_bounds__(kE2Threads, 4) k_edge_pass_v2(PlanView pv, Cal
 #pragma unroll
             for (int a = 0; a < 6; ++a) Eis[a] -= Ei[a];
             const int lj = slj[pl];
+            const bool head = pl == pw0 || lj != slj[pl - 1];                   // first position of a slot run
             if (lj == li) {                                                     // self edge: its j side feeds the source slot too
 #pragma unroll
               for (int a = 0; a < 6; ++a) Eis[a] += Ej[a];
-            } else if (have) {
-              const bool fj = sfj[pl] != 0;
-              float *col = Eb + (size_t)(6 * lj) * Ts + (t - gt0);
+            } else {
+              if (head) {
 #pragma unroll
-              for (int a = 0; a < 6; ++a) col[(size_t)a * Ts] = fj ? Ej[a] : 0.0f;
+                for (int a = 0; a < 6; ++a) Ejs[a] = Ej[a];
+              } else {
+#pragma unroll
+                for (int a = 0; a < 6; ++a) Ejs[a] += Ej[a];
+              }
+              if (have && (pl + 1 == pw1 || slj[pl + 1] != lj)) {               // last position of the run: the one store
+                const bool fj = sfj[pl] != 0;
+                float *col = Eb + (size_t)(6 * lj) * Ts + (t - gt0);
+#pragma unroll
+                for (int a = 0; a < 6; ++a) col[(size_t)a * Ts] = fj ? Ejs[a] : 0.0f;
+              }
             }
+            if (head) hd = pl;
             __syncwarp();
             if (lane < kAccComps) {                                             // sum of component `lane` over the 32 tracks
               const float4 *row = reinterpret_cast<const float4 *>(red + lane * kE2RedStride);
               float4 s4 = row[0];
 #pragma unroll
               for (int k = 1; k < 8; ++k) { const float4 v = row[k]; s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w; }
-              sacc[pl * kE2AccStride + lane] = (s4.x + s4.y) + (s4.z + s4.w);
+              const float sv = (s4.x + s4.y) + (s4.z + s4.w);                   // positions of one (i, j) pair share a row
+              sacc[hd * kE2AccStride + lane] = head ? sv : sacc[hd * kE2AccStride + lane] + sv;
             }
             __syncwarp();
           }
@@ -502,7 +551,7 @@ __global__ void __launch_bounds__(kE2Threads, 4) k_edge_pass_v2(PlanView pv, Cal
       }
     }
     if (!STRUCT_ONLY) {
-      // ---- flush of this block of positions: add the warps' sums (fp64), map to the i side, fp64 atomics ----
+      // ---- flush of this block of positions: add the slices' sums (fp64), map to the i side, fp64 atomics ----
       __syncthreads();
       constexpr int NT = kE2Threads;
       double *sumD = reinterpret_cast<double *>(scratch);          // [kE2FlushPos][27]
@@ -510,18 +559,18 @@ __global__ void __launch_bounds__(kE2Threads, 4) k_edge_pass_v2(PlanView pv, Cal
       double *outD = ABs + kE2FlushPos * 36;                       // [kE2FlushPos][90]
       const int pi = slot_pose[li];
       const int ri = 6 * (pi - cv.fixedp);
-      for (int fb = 0; fb < np; fb += kE2FlushPos) {
-        const int nq = min(kE2FlushPos, np - fb);
+      for (int fb = 0; fb < nh; fb += kE2FlushPos) {              // over the run heads: one (i, j) pair each
+        const int nq = min(kE2FlushPos, nh - fb);
         for (int x = tau; x < nq * kAccComps; x += NT) {
           const int pl = x / kAccComps, k = x - pl * kAccComps;
           double sv = 0.0;
-          for (int ww = 0; ww < nW; ++ww) sv += (double)sacc_all[(ww * kE2PosBlock + fb + pl) * kE2AccStride + k];
+          for (int ww = 0; ww < nS; ++ww) sv += (double)sacc_all[(ww * kE2PosBlock + hlist[fb + pl]) * kE2AccStride + k];
           sumD[x] = sv;
         }
         __syncthreads();
         for (int x = tau; x < nq * 7; x += NT) {                   // (position, column c of Bjj) and (position, vj)
           const int pl = x / 7, c = x - pl * 7;
-          const float *cs = sconst + (fb + pl) * kPosFloats;
+          const float *cs = sconst + hlist[fb + pl] * kPosFloats;
           const Vec3 tt{cs[9], cs[10], cs[11]};
           const double *Sm = sumD + pl * kAccComps;
           double *o = outD + pl * kFlushOuts;
@@ -545,22 +594,23 @@ __global__ void __launch_bounds__(kE2Threads, 4) k_edge_pass_v2(PlanView pv, Cal
         __syncthreads();
         for (int x = tau; x < nq * 6; x += NT) {                   // (position, row a): Bii = (A Bjj) A^T, ba.py:279
           const int pl = x / 6, a = x - pl * 6;
-          const float *cs = sconst + (fb + pl) * kPosFloats;
+          const float *cs = sconst + hlist[fb + pl] * kPosFloats;
           const Vec3 tt{cs[9], cs[10], cs[11]};
           double rowv[6], res[6];
 #pragma unroll
           for (int c = 0; c < 6; ++c) rowv[c] = ABs[pl * 36 + a * 6 + c];
           adjT_apply_d(cs, tt, rowv, res);
           double *o = outD + pl * kFlushOuts + 21;
-          for (int b2 = 0; b2 <= a; ++b2) o[tri(a, b2)] = res[b2];
+#pragma unroll
+          for (int b2 = 0; b2 < 6; ++b2) if (b2 <= a) o[tri(a, b2)] = res[b2];
         }
         __syncthreads();
         // Bjj, Bij (+ Bji), vj: one atomic per (position, entry); Bii, vi: summed over the positions first
         for (int x = tau; x < nq * kFlushOuts; x += NT) {
           const int pl = x / kFlushOuts, o = x - pl * kFlushOuts;
           if ((o >= 21 && o < 42) || o >= 84) continue;
-          const int pj = pv.pat_j[pat0 + pb + fb + pl];
-          const bool f_j = sfj[fb + pl] != 0;
+          const int pj = spj[hlist[fb + pl]];
+          const bool f_j = sfj[hlist[fb + pl]] != 0;
           const int rj = 6 * (pj - cv.fixedp);
           const double val = outD[x];
           if (o < 21) {
@@ -586,9 +636,27 @@ __global__ void __launch_bounds__(kE2Threads, 4) k_edge_pass_v2(PlanView pv, Cal
         __syncthreads();
       }
     }
+    pb += np;
   }
 
-  if (have) {
+  // ---- per track: the KP partial sums meet in shared memory (fixed order), then Q, w and the source slot's E ----
+  if (KP > 1) {
+    __syncthreads();
+    float *tp = scratch + warp * (8 * 32);                         // [8][32] per warp
+    tp[lane] = C; tp[32 + lane] = w;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) tp[(2 + a) * 32 + lane] = Eis[a];
+    __syncthreads();
+    if (sp == 0) {
+      for (int k = 1; k < KP; ++k) {
+        const float *o = scratch + (warp + k) * (8 * 32);
+        C += o[lane]; w += o[32 + lane];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) Eis[a] += o[(2 + a) * 32 + lane];
+      }
+    }
+  }
+  if (have && sp == 0) {
     if (!STRUCT_ONLY) {
       float *col = Eb + (size_t)(6 * li) * Ts + (t - gt0);
 #pragma unroll
@@ -597,6 +665,7 @@ __global__ void __launch_bounds__(kE2Threads, 4) k_edge_pass_v2(PlanView pv, Cal
     // damped inverse Q and prior-adjusted w (ba.py:296-311; BA: :184)
     const float lam = cv.lmbda_vec ? cv.lmbda_vec[t] : cv.lmbda;
     if (cv.monodisp) {
+      const float md = __ldg(cv.monodisp + (size_t)__ldg(pv.kx + t));
       const float mk = md > 1e-2f ? 1.0f : 0.0f;
       C = C + mk * cv.alpha;
       C = C + lam;
@@ -717,10 +786,13 @@ __global__ void k_track_q(PlanView pv, CallView cv) {
 //   tracks in fp32 registers and the runs are added into fp64 registers (the subtraction B - E Q E^T
 //   cancels heavily, so the long sums must not round at fp32); one flush of fp64 atomics per unit.
 // =================================================================================================
-constexpr int kSchurRun = 8;
+constexpr int kSchurRun = 16;     // tracks per fp32 run (even)
+constexpr int kSchurStages = 3;   // sub-tiles of E in flight (cp.async ring)
+constexpr int kSchurPad = 2;      // floats of padding per staged row: 8-byte loads of neighbouring slots hit distinct banks
 
-constexpr int kSchurStages = 3;   // sub-tiles of E rows in flight (cp.async ring)
-
+// Stage layout: E entries [rowlen][tile + kSchurPad] (entry-major like global E: the copy is 8-byte cp.async along
+// the tracks, coalesced), then (Q, w) [tile] float2. A thread reads the two tracks (k, k+1) of one entry with one
+// 8-byte load.
 __global__ void __launch_bounds__(kSchurThreads, 2) k_schur(PlanView pv, CallView cv, int tile_tracks) {
   constexpr int NT = kSchurThreads;
   extern __shared__ __align__(16) float smem[];
@@ -733,28 +805,39 @@ __global__ void __launch_bounds__(kSchurThreads, 2) k_schur(PlanView pv, CallVie
   const int rowlen = 6 * W;
   const int *slot_pose = pv.slot_pose + 2 * pv.g_pat[g];
   const float *Erows = cv.Est + pv.g_eoff[g];
-  const int stage_floats = tile_tracks * (rowlen + 2);            // [tile][rowlen] E rows + [tile] float2 (Q, w)
+  const int Ts = (pv.g_t0[g + 1] - gt0 + 3) & ~3;
+  const int ts = tile_tracks + kSchurPad;
+  const int stage_floats = rowlen * ts + 2 * tile_tracks;
   const int npairs = W * (W + 1) / 2;
   const int nst = (t1 - t0 + tile_tracks - 1) / tile_tracks;
+  const int half = tile_tracks >> 1;
 
-  // stage st <- E entries and (Q, w) of tracks [t0 + st*tile, ...). Global E is entry-major ([6W][Ts], coalesced
-  // along tracks); the stage is track-major ([tile][rowlen]) so that a thread reads the 6-vectors of its two slots
-  // with three 8-byte loads each: the copy transposes (4-byte cp.async, consecutive threads = consecutive tracks).
-  const int Ts = (pv.g_t0[g + 1] - gt0 + 3) & ~3;
   auto issue = [&](int st) {
     if (st < nst) {
       const int tt = t0 + st * tile_tracks, nt = min(tile_tracks, t1 - tt);
       float *dst = smem + (size_t)(st % kSchurStages) * stage_floats;
-      const float *src = Erows + (tt - gt0);
-      for (int o = tau; o < rowlen * tile_tracks; o += NT) {
-        const int r = o / tile_tracks, k = o - r * tile_tracks;
-        if (k < nt) cp_async4(dst + k * rowlen + r, src + (size_t)r * Ts + k);
+      const float *src = Erows + (tt - gt0);                       // (tt - gt0) is a multiple of 4 (plan units)
+      const int nh = (nt + 1) >> 1;                                // track pairs to copy (the odd tail reads row padding)
+      for (int o = tau; o < rowlen * half; o += NT) {
+        const int r = o / half, k2 = o - r * half;
+        if (k2 < nh) cp_async8(dst + r * ts + 2 * k2, src + (size_t)r * Ts + 2 * k2);
       }
-      float2 *dq = reinterpret_cast<float2 *>(dst + (size_t)tile_tracks * rowlen);
-      for (int o = tau; o < nt; o += NT) cp_async8(dq + o, cv.Qw + tt + o);
+      float2 *dq = reinterpret_cast<float2 *>(dst + (size_t)rowlen * ts);
+      for (int o = tau; o < tile_tracks; o += NT) {
+        if (o < nt) cp_async8(dq + o, cv.Qw + tt + o);
+        else dq[o] = make_float2(0.0f, 0.0f);                      // tracks past the unit contribute nothing
+      }
     }
     cp_async_commit();
   };
+  // E entries past the unit's last track are never copied: start from finite values (they meet Q = 0)
+  for (int o = tau; o < kSchurStages * stage_floats; o += NT) smem[o] = 0.0f;
+
+  // threads of the warps that hold no pair (first pair batch) take y -= E Q w (ba.py:322) while the others
+  // multiply; without such warps every thread does it before its pairs
+  const int pair_warps = (min(npairs, NT) + 31) >> 5;
+  const bool y_idle = pair_warps < NT / 32;
+  const int y_t0 = y_idle ? 32 * pair_warps : 0, y_nt = NT - y_t0;
 
   for (int pb = 0; pb < npairs; pb += NT) {
     const int x = pb + tau;
@@ -770,7 +853,7 @@ __global__ void __launch_bounds__(kSchurThreads, 2) k_schur(PlanView pv, CallVie
 #pragma unroll
     for (int k = 0; k < 36; ++k) acc[k] = 0.0;
 
-    __syncthreads();                               // ring free (previous pair batch done)
+    __syncthreads();                               // ring free (previous pair batch done) / zero fill visible
     issue(0);
     issue(1);
     for (int st = 0; st < nst; ++st) {
@@ -778,35 +861,44 @@ __global__ void __launch_bounds__(kSchurThreads, 2) k_schur(PlanView pv, CallVie
       __syncthreads();                             // stage st landed for everyone; stage st-1 fully consumed
       issue(st + 2);
       const int nt = min(tile_tracks, t1 - (t0 + st * tile_tracks));
+      const int nt2 = (nt + 1) & ~1;
       const float *Es = smem + (size_t)(st % kSchurStages) * stage_floats;
-      const float2 *qw = reinterpret_cast<const float2 *>(Es + (size_t)tile_tracks * rowlen);
-      if (pb == 0) {                              // y -= E Q w   (ba.py:322)
-        for (int r = tau; r < rowlen; r += NT) {
+      const float2 *qw = reinterpret_cast<const float2 *>(Es + (size_t)rowlen * ts);
+      if (pb == 0 && tau >= y_t0) {                // y -= E Q w   (ba.py:322)
+        for (int r = tau - y_t0; r < rowlen; r += y_nt) {
           const int pose = slot_pose[r / 6];
           if (pose_free(pose, cv)) {
-            double s = 0.0;
-            for (int k = 0; k < nt; ++k) s += (double)(qw[k].x * qw[k].y * Es[k * rowlen + r]);
-            red_add(cv.y + 6 * (pose - cv.fixedp) + (r % 6), -s);
+            const float *er = Es + r * ts;
+            double s2 = 0.0;
+            for (int k0 = 0; k0 < nt; k0 += 8) {
+              float ps = 0.0f;
+              const int k1 = min(k0 + 8, nt);
+              for (int k = k0; k < k1; ++k) ps += qw[k].x * qw[k].y * er[k];
+              s2 += (double)ps;
+            }
+            red_add(cv.y + 6 * (pose - cv.fixedp) + (r % 6), -s2);
           }
         }
       }
       if (have) {
-        for (int k0 = 0; k0 < nt; k0 += kSchurRun) {
+        const float *ea = Es + 6 * a * ts, *eb = Es + 6 * b * ts;
+        for (int k0 = 0; k0 < nt2; k0 += kSchurRun) {
           float part[36];
 #pragma unroll
           for (int k = 0; k < 36; ++k) part[k] = 0.0f;
-          const int k1 = min(k0 + kSchurRun, nt);
-          for (int k = k0; k < k1; ++k) {
-            const float q = qw[k].x;
-            const float2 *ea = reinterpret_cast<const float2 *>(Es + k * rowlen + 6 * a);
-            const float2 *eb = reinterpret_cast<const float2 *>(Es + k * rowlen + 6 * b);
-            const float2 a01 = ea[0], a23 = ea[1], a45 = ea[2], b01 = eb[0], b23 = eb[1], b45 = eb[2];
-            const float va[6] = {q * a01.x, q * a01.y, q * a23.x, q * a23.y, q * a45.x, q * a45.y};
-            const float vb[6] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
+          const int k1 = min(k0 + kSchurRun, nt2);
+          for (int k = k0; k < k1; k += 2) {
+            const float q0 = qw[k].x, q1 = qw[k + 1].x;
+            float2 vb[6];
 #pragma unroll
-            for (int c = 0; c < 6; ++c)
+            for (int c = 0; c < 6; ++c) vb[c] = *reinterpret_cast<const float2 *>(eb + c * ts + k);
 #pragma unroll
-              for (int e2 = 0; e2 < 6; ++e2) part[c * 6 + e2] += va[c] * vb[e2];
+            for (int c = 0; c < 6; ++c) {
+              const float2 v = *reinterpret_cast<const float2 *>(ea + c * ts + k);
+              const float vx = q0 * v.x, vy = q1 * v.y;
+#pragma unroll
+              for (int e2 = 0; e2 < 6; ++e2) part[c * 6 + e2] += vx * vb[e2].x + vy * vb[e2].y;
+            }
           }
 #pragma unroll
           for (int k = 0; k < 36; ++k) acc[k] += (double)part[k];
@@ -1081,44 +1173,68 @@ __device__ __forceinline__ void pose_retr_one(const CallView &cv, int i) {
   pose_store(r, cv.poses_out + 7 * (size_t)i);
 }
 
-// blocks [0, nb_back): one thread per patch; blocks beyond: pose retraction T <- Exp(dx) T for every pose of the
-// buffer, dx = 0 outside the window (ba.py:47-49,336-337; lietorch/groups.py:153-156), when retr_n > 0
-__global__ void __launch_bounds__(256) k_backsub(PlanView pv, CallView cv, int use_dx, int nb_back, int retr_n) {
-  if ((int)blockIdx.x >= nb_back) {
-    const int i = ((int)blockIdx.x - nb_back) * blockDim.x + threadIdx.x;
+// Three kinds of blocks in one launch:
+//   [0, nb_trk)            32 consecutive tracks per CTA, lane <-> track (coalesced entry-major E reads), the 8 warps
+//                          split the slots of the track's group; partial dots meet in shared memory in fixed order;
+//                          warp 0 writes dZ and the three floats of the track's patch;
+//   [nb_trk, nb_trk+nb_cp) one thread per patch: patches without a track are copied with the clamp;
+//   beyond                 pose retraction T <- Exp(dx) T for every pose of the buffer, dx = 0 outside the window
+//                          (ba.py:47-49,336-337; lietorch/groups.py:153-156), when retr_n > 0
+__global__ void __launch_bounds__(256) k_backsub(PlanView pv, CallView cv, int use_dx, int nb_trk, int nb_cp, int retr_n) {
+  __shared__ double part[8][32];
+  const int bid = blockIdx.x;
+  if (bid >= nb_trk + nb_cp) {
+    const int i = (bid - nb_trk - nb_cp) * blockDim.x + threadIdx.x;
     if (i < retr_n) pose_retr_one(cv, i);
     return;
   }
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= pv.NM) return;
-  const float px = cv.patches[3 * (size_t)k], py = cv.patches[3 * (size_t)k + 1];
-  float dsp = cv.patches[3 * (size_t)k + 2];
-  const int t = pv.patch_track[k];
-  if (t >= 0) {
-    const float2 qw = cv.Qw[t];
+  if (bid >= nb_trk) {
+    const int k = (bid - nb_trk) * blockDim.x + threadIdx.x;
+    if (k >= pv.NM || pv.patch_track[k] >= 0) return;
+    cv.patches_out[3 * (size_t)k] = cv.patches[3 * (size_t)k];
+    cv.patches_out[3 * (size_t)k + 1] = cv.patches[3 * (size_t)k + 1];
+    cv.patches_out[3 * (size_t)k + 2] = fminf(fmaxf(cv.patches[3 * (size_t)k + 2], 1e-3f), 10.0f);   // clamp hits every patch, ba.py:333
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = bid * 32 + lane;
+  const bool have = t < pv.m;
+  if (use_dx) {
     double dot = 0.0;
-    if (use_dx) {
+    if (have) {
       const int g = pv.t_grp[t];
       const int W = pv.g_W[g], gt0 = pv.g_t0[g];
       const int Ts = (pv.g_t0[g + 1] - gt0 + 3) & ~3;
       const int *slot_pose = pv.slot_pose + 2 * pv.g_pat[g];
       const float *col = cv.Est + pv.g_eoff[g] + (t - gt0);
-      for (int sl = 0; sl < W; ++sl) {
+      for (int sl = warp; sl < W; sl += 8) {
         const int pose = slot_pose[sl];
         if (!pose_free(pose, cv)) continue;
         const double *dx = cv.dX + 6 * (pose - cv.fixedp);
         const float *e = col + (size_t)(6 * sl) * Ts;
+        double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) dot += (double)e[(size_t)c * Ts] * dx[c];
+        for (int c = 0; c < 6; c += 2) { d0 += (double)e[(size_t)c * Ts] * dx[c]; d1 += (double)e[(size_t)(c + 1) * Ts] * dx[c + 1]; }
+        dot += d0 + d1;
       }
+    }
+    part[warp][lane] = dot;
+    __syncthreads();
+  }
+  if (warp == 0 && have) {
+    const float2 qw = cv.Qw[t];
+    double dot = 0.0;
+    if (use_dx) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dot += part[k][lane];
     }
     const float dz = (float)((double)qw.x * ((double)qw.y - dot));
     cv.dZ[t] = dz;
-    dsp += dz;
+    const size_t k = (size_t)pv.kx[t];
+    cv.patches_out[3 * k] = cv.patches[3 * k];
+    cv.patches_out[3 * k + 1] = cv.patches[3 * k + 1];
+    cv.patches_out[3 * k + 2] = fminf(fmaxf(cv.patches[3 * k + 2] + dz, 1e-3f), 10.0f);
   }
-  cv.patches_out[3 * (size_t)k] = px;
-  cv.patches_out[3 * (size_t)k + 1] = py;
-  cv.patches_out[3 * (size_t)k + 2] = fminf(fmaxf(dsp, 1e-3f), 10.0f);          // clamp hits every patch, ba.py:333
 }
 
 // ---- debug: expand the lower (band) storage to a dense symmetric matrix, cast fp64 -> fp32 --------
@@ -1176,8 +1292,8 @@ extern "C" int ba_assemble(BaPlan *pl, const BaProblem *pb, void *stream_) {
   }
   static bool edge2_attr_set = false;
   if (!edge2_attr_set) {
-    BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdge2SmemBytes));
-    BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdge2SmemBytes));
+    BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1)));
+    BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1)));
     edge2_attr_set = true;
   }
   // regular groups (every SLAM graph): lane-per-track kernel; irregular groups: the generic kernels (each kernel
@@ -1190,14 +1306,14 @@ extern "C" int ba_assemble(BaPlan *pl, const BaProblem *pb, void *stream_) {
   }
   if (so) {
     BA_MARK(pl, BA_STAGE_EDGE, s);
-    if (any_regular) { k_edge_pass_v2<true><<<pv.n_xchunks, kE2Threads, kEdge2SmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
+    if (any_regular) { k_edge_pass_v2<true><<<pv.n_xchunks, kE2Threads, edge2_smem_bytes(pv.e2_kp), s>>>(pv, cv); BA_LAUNCH_CHECK(); }
     if (any_irregular) { k_edge_pass<true><<<pv.n_chunks, kEdgeThreads, kEdgeSmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
     if (has_long) { k_edge_pass_long<true><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
   } else {
     BA_MARK(pl, BA_STAGE_ZERO, s);
     BA_CUDA(cudaMemsetAsync(cv.S, 0, (size_t)((cv.y - cv.S) + cv.M) * sizeof(double), s));
     BA_MARK(pl, BA_STAGE_EDGE, s);
-    if (any_regular) { k_edge_pass_v2<false><<<pv.n_xchunks, kE2Threads, kEdge2SmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
+    if (any_regular) { k_edge_pass_v2<false><<<pv.n_xchunks, kE2Threads, edge2_smem_bytes(pv.e2_kp), s>>>(pv, cv); BA_LAUNCH_CHECK(); }
     if (any_irregular) { k_edge_pass<false><<<pv.n_chunks, kEdgeThreads, kEdgeSmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
     if (has_long) { k_edge_pass_long<false><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
   }
@@ -1208,9 +1324,9 @@ extern "C" int ba_assemble(BaPlan *pl, const BaProblem *pb, void *stream_) {
   BA_MARK(pl, BA_STAGE_SCHUR, s);
   if (!so) {
     const int rowmax = 6 * pl->info.max_slots;
-    int tile = (int)((24 * 1024 / sizeof(float)) / (rowmax + 2));       // per stage; kSchurStages stages in flight
-    tile = tile < 1 ? 1 : (tile > 32 ? 32 : tile);
-    const size_t smem = (size_t)kSchurStages * tile * (rowmax + 2) * sizeof(float);
+    int tile = 32;                                                       // per stage; kSchurStages stages in flight
+    while (tile > 4 && (size_t)kSchurStages * (rowmax * (tile + kSchurPad) + 2 * tile) * sizeof(float) > 96 * 1024) tile -= 4;
+    const size_t smem = (size_t)kSchurStages * (rowmax * (tile + kSchurPad) + 2 * tile) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
       BA_CUDA(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1266,8 +1382,8 @@ extern "C" int ba_solve_update(BaPlan *pl, const BaProblem *pb, void *stream_) {
   }
   BA_MARK(pl, BA_STAGE_BACKSUB, s);
   {
-    const int nb_back = (pv.NM + 255) / 256, nb_retr = so ? 0 : (pv.N + 255) / 256;
-    k_backsub<<<nb_back + nb_retr, 256, 0, s>>>(pv, cv, so ? 0 : 1, nb_back, so ? 0 : pv.N); BA_LAUNCH_CHECK();
+    const int nb_trk = (pv.m + 31) / 32, nb_cp = (pv.NM + 255) / 256, nb_retr = so ? 0 : (pv.N + 255) / 256;
+    k_backsub<<<nb_trk + nb_cp + nb_retr, 256, 0, s>>>(pv, cv, so ? 0 : 1, nb_trk, nb_cp, so ? 0 : pv.N); BA_LAUNCH_CHECK();
   }
   BA_MARK(pl, BA_STAGE_RETR, s);
   if (so) BA_CUDA(cudaMemcpyAsync(pb->poses_out, pb->poses, (size_t)pv.N * 7 * sizeof(float), cudaMemcpyDeviceToDevice, s));

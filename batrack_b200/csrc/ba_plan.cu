@@ -145,7 +145,7 @@ __global__ void k_group_slots(const int *__restrict__ g_t0, const int *__restric
                               int *__restrict__ g_nm, int *__restrict__ ms_ptr, int *__restrict__ ms_slot,
                               int *__restrict__ pat_ri, int *__restrict__ pat_rj,
                               int *__restrict__ g_W, long long *__restrict__ g_esz, int *__restrict__ g_reg,
-                              int *__restrict__ meta) {
+                              int *__restrict__ pat_ps, int *__restrict__ meta) {
   extern __shared__ unsigned sm[];
   const int g = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int nwords = (N + 31) >> 5;
@@ -228,12 +228,23 @@ __global__ void k_group_slots(const int *__restrict__ g_t0, const int *__restric
     g_W[g] = W;
     // E rows are stored entry-major ("SoA"): [6 W][Ts] floats, Ts = T rounded up to 4 (16-byte rows)
     g_esz[g] = (long long)((T + 3) & ~3) * 6 * W;
-    // "regular" group (every SLAM graph: one source frame per track, distinct target frames): all positions share
-    // the source slot and no other slot is fed twice -> the lane-per-track edge pass (k_edge_pass_v2) applies
-    bool reg = true;
+    // positions ordered by (target slot, position): the walk order of the lane-per-track edge pass, in which the
+    // positions that feed one E slot are consecutive (a SLAM graph observes a (patch, frame) pair several times)
+    int maxrun = 0;
+    {
+      int xo = 0;
+      for (int s = 0; s < W; ++s) {
+        int run = 0;
+        for (int x = sp[s]; x < sp[s + 1]; ++x)
+          if (it[x] & 1) { pat_ps[pat0 + xo++] = it[x] >> 1; ++run; }
+        maxrun = max(maxrun, run);
+      }
+    }
+    // "regular" group (every SLAM graph: one source frame per track): all positions share the source slot, and no
+    // target slot is fed more than kMaxSlotRun times -> the lane-per-track edge pass (k_edge_pass_v2) applies
+    bool reg = maxrun <= kMaxSlotRun;
     const int s0 = pat_li[pat0];
     for (int p = 0; p < d; ++p) reg = reg && pat_li[pat0 + p] == s0;
-    for (int s = 0; s < W; ++s) reg = reg && (s == s0 || sp[s + 1] - sp[s] < 2);
     g_reg[g] = reg ? 1 : 0;
     if (!reg) { atomicAdd(&meta[META_NIRREG], 1); atomicMax(&meta[META_DMAX_IRREG], d); }
     atomicMax(&meta[META_WMAX], W);
@@ -408,8 +419,9 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     k_fill_tracks<<<cdiv(E, TB), TB, 0, s>>>(tflag, tinc, skey, nE, kx, tptr); PL_LAUNCH();
     k_group_flags<<<cdiv(E, TB), TB, 0, s>>>(tinc, tptr, sij, nE, gflag, meta); PL_LAUNCH();
     PL_CUDA(inclusive_sum(sc, gflag, ginc, m, s));
-    int G = 0;
+    int G = 0, hmeta_dmax = 0;
     PL_CUDA(cudaMemcpyAsync(&G, ginc + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    PL_CUDA(cudaMemcpyAsync(&hmeta_dmax, meta + META_DMAX, sizeof(int), cudaMemcpyDeviceToHost, s));
     PL_CUDA(cudaStreamSynchronize(s));
 
     int *g_t0, *g_pat, *g_W, *g_d, *g_reg;
@@ -431,9 +443,14 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     if (const char *e = getenv("BA_SCHUR_TU")) tu = std::max(1, atoi(e));
     int *cflag, *cinc;
     PL_CUDA(sc.get(&cflag, m)); PL_CUDA(sc.get(&cinc, m));
-    // lane-per-track edge pass: one CTA of kEdge2Warps warps per <= 32 * kEdge2Warps tracks of a group
-    int tx = 32 * kEdge2Warps;
-    if (const char *e = getenv("BA_EDGE2_TX")) tx = std::max(32, std::min(32 * kEdge2Warps, atoi(e)));
+    // lane-per-track edge pass: a CTA of kEdge2Warps warps = KT track slices x KP position splits. One split is the
+    // cheapest per edge (fewest flushes; measured at 256 KF / 64k tracks: 44 us vs 54 / 60 us with 2 / 4 splits);
+    // graphs with few tracks split the positions until the machine sees ~12 warps per SM (25-frame window, 5200
+    // tracks x <= 72 edges: 70 / 53 / 39 us with 2 / 4 / 8 splits).
+    int kp = 1;
+    while (kp < kEdge2Warps && (int64_t)cdiv(m, 32) * kp < 12 * sms && cdiv(hmeta_dmax, kp) > 2) kp *= 2;
+    if (const char *e = getenv("BA_EDGE2_KP")) { int v2 = atoi(e); if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8) kp = v2; }
+    const int tx = 32 * (kEdge2Warps / kp);
     int counts[3] = {0, 0, 0};
     int *unit_t0[3], *unit_grp[3];
     for (int pass = 0; pass < 3; ++pass) {
@@ -449,10 +466,10 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     int pat_total = 0;
     PL_CUDA(cudaMemcpyAsync(&pat_total, g_pat + G, sizeof(int), cudaMemcpyDeviceToHost, s));
     PL_CUDA(cudaStreamSynchronize(s));
-    int *pat_i, *pat_j, *pat_li, *pat_lj, *slot_pose, *slot_ptr, *slot_items, *g_nm, *ms_ptr, *ms_slot, *pat_ri, *pat_rj;
+    int *pat_i, *pat_j, *pat_li, *pat_lj, *slot_pose, *slot_ptr, *slot_items, *g_nm, *ms_ptr, *ms_slot, *pat_ri, *pat_rj, *pat_ps;
     PL_CUDA(own(pl, &g_nm, G)); PL_CUDA(own(pl, &pat_ri, pat_total)); PL_CUDA(own(pl, &pat_rj, pat_total));
     PL_CUDA(own(pl, &ms_slot, 2 * (size_t)pat_total)); PL_CUDA(own(pl, &ms_ptr, 2 * (size_t)pat_total + G + 1));
-    PL_CUDA(own(pl, &pat_i, pat_total)); PL_CUDA(own(pl, &pat_j, pat_total));
+    PL_CUDA(own(pl, &pat_i, pat_total)); PL_CUDA(own(pl, &pat_j, pat_total)); PL_CUDA(own(pl, &pat_ps, pat_total));
     PL_CUDA(own(pl, &pat_li, pat_total)); PL_CUDA(own(pl, &pat_lj, pat_total));
     PL_CUDA(own(pl, &slot_pose, 2 * (size_t)pat_total)); PL_CUDA(own(pl, &slot_items, 2 * (size_t)pat_total));
     PL_CUDA(own(pl, &slot_ptr, 2 * (size_t)pat_total + G + 1));
@@ -460,7 +477,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
       int nwords = (N + 31) / 32;
       size_t smem = (size_t)(2 * nwords + 1) * sizeof(int);
       k_group_slots<<<G, 128, smem, s>>>(g_t0, g_pat, tptr, sij, N, pat_i, pat_j, pat_li, pat_lj, slot_pose,
-                                         slot_ptr, slot_items, g_nm, ms_ptr, ms_slot, pat_ri, pat_rj, g_W, g_esz, g_reg, meta); PL_LAUNCH();
+                                         slot_ptr, slot_items, g_nm, ms_ptr, ms_slot, pat_ri, pat_rj, g_W, g_esz, g_reg, pat_ps, meta); PL_LAUNCH();
     }
     k_zero_last<<<1, 1, 0, s>>>(g_esz, G); PL_LAUNCH();
     PL_CUDA(exclusive_sum(sc, g_esz, g_eoff, G + 1, s));
@@ -477,8 +494,8 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     v.slot_pose = slot_pose; v.slot_ptr = slot_ptr; v.slot_items = slot_items;
     v.g_nm = g_nm; v.ms_ptr = ms_ptr; v.ms_slot = ms_slot; v.pat_ri = pat_ri; v.pat_rj = pat_rj; v.dmax = hmeta[META_DMAX];
     v.c_t0 = unit_t0[0]; v.c_grp = unit_grp[0]; v.u_t0 = unit_t0[1]; v.u_grp = unit_grp[1];
-    v.x_t0 = unit_t0[2]; v.x_grp = unit_grp[2]; v.n_xchunks = counts[2];
-    v.g_reg = g_reg; v.n_irregular = hmeta[META_NIRREG]; v.dmax_irregular = hmeta[META_DMAX_IRREG];
+    v.x_t0 = unit_t0[2]; v.x_grp = unit_grp[2]; v.n_xchunks = counts[2]; v.e2_kp = kp;
+    v.pat_ps = pat_ps; v.g_reg = g_reg; v.n_irregular = hmeta[META_NIRREG]; v.dmax_irregular = hmeta[META_DMAX_IRREG];
     {
       int *ptk;
       PL_CUDA(own(pl, &ptk, NM));
