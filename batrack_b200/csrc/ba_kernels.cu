@@ -897,7 +897,7 @@ __global__ void __launch_bounds__(kSchurThreads, 2) k_schur(PlanView pv, CallVie
               const float2 v = *reinterpret_cast<const float2 *>(ea + c * ts + k);
               const float vx = q0 * v.x, vy = q1 * v.y;
 #pragma unroll
-              for (int e2 = 0; e2 < 6; ++e2) part[c * 6 + e2] += vx * vb[e2].x + vy * vb[e2].y;
+              for (int e2 = 0; e2 < 6; ++e2) part[c * 6 + e2] = fmaf(vy, vb[e2].y, fmaf(vx, vb[e2].x, part[c * 6 + e2]));
             }
           }
 #pragma unroll
@@ -1324,8 +1324,9 @@ extern "C" int ba_assemble(BaPlan *pl, const BaProblem *pb, void *stream_) {
   BA_MARK(pl, BA_STAGE_SCHUR, s);
   if (!so) {
     const int rowmax = 6 * pl->info.max_slots;
-    int tile = 32;                                                       // per stage; kSchurStages stages in flight
-    while (tile > 4 && (size_t)kSchurStages * (rowmax * (tile + kSchurPad) + 2 * tile) * sizeof(float) > 96 * 1024) tile -= 4;
+    int tile = 64;                                                       // per stage; kSchurStages stages in flight; 2 CTAs per SM
+    if (const char *e = getenv("BA_SCHUR_TILE")) tile = std::max(4, atoi(e) & ~3);
+    while (tile > 4 && (size_t)kSchurStages * (rowmax * (tile + kSchurPad) + 2 * tile) * sizeof(float) > 100 * 1024) tile -= 4;
     const size_t smem = (size_t)kSchurStages * (rowmax * (tile + kSchurPad) + 2 * tile) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {

@@ -520,16 +520,37 @@ __global__ void __launch_bounds__(kMmaHwThreads, 1) k_solve_band_mma(CallView cv
     //      8J..8J+7 of L restricted to columns [8(J-15), 8J) plus W_J. On side 1 the middle rows J >= c1 were not
     //      factored here: their solution is given (x_mid from side 0) and only their coupling to the columns this
     //      side owns (which it did compute) is applied. ----
+    // Each thread copies the same (row-in-tile, column) elements of every stage; their source moves by a fixed
+    // stride per tile row, so everything but the two edge tests is computed once here.
+    int sl_kind[4], sl_doff[4], sl_xc[4];                          // 0 none, 1 band element, 2 always zero, 3 element of W_J
+    long long sl_src[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int o = tau + k * kMmaThreads;
+      sl_kind[k] = 0; sl_doff[k] = 0; sl_xc[k] = 0; sl_src[k] = 0;
+      if (o < 8 * 120) {
+        const int gg = o / 120, xcol = o - gg * 120;
+        sl_doff[k] = gg * 128 + xcol;
+        sl_xc[k] = xcol - 120;                                     // column = 8 J + sl_xc
+        sl_kind[k] = (120 + gg - xcol <= bw) ? 1 : 2;              // r - c does not depend on J
+        sl_src[k] = (long long)gg * bw + (xcol - 120) + bw;        // Lg(8J + gg, 8J + xcol - 120) - J (8 bw + 8)
+      } else if (o < 8 * 120 + 64) {
+        sl_kind[k] = 3; sl_doff[k] = 8 * 128 + (o - 8 * 120); sl_src[k] = o - 8 * 120;
+      }
+    }
     auto stage_load = [&](int J, int sidx) {
       double *dst = Lst + (size_t)sidx * (8 * 128 + 64);
-      for (int o = tau; o < 8 * 120 + 64; o += kMmaThreads) {
-        if (o < 8 * 120) {
-          const int gg = o / 120, xcol = o - gg * 120;
-          const int r = 8 * J + gg, c = 8 * (J - 15) + xcol;
-          if (c >= 0 && c < 8 * ncols && r - c <= bw) cp_async8_d(dst + gg * 128 + xcol, L + Lg(r, c));
-          else dst[gg * 128 + xcol] = 0.0;
-        } else if (J < ncols) {
-          cp_async8_d(dst + 8 * 128 + (o - 8 * 120), Wg + (size_t)J * 64 + (o - 8 * 120));
+      const double *Lj = L + (long long)J * (8 * bw + 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (sl_kind[k] == 1) {
+          const int c = 8 * J + sl_xc[k];
+          if (c >= 0 && c < 8 * ncols) cp_async8_d(dst + sl_doff[k], Lj + sl_src[k]);
+          else dst[sl_doff[k]] = 0.0;
+        } else if (sl_kind[k] == 2) {
+          dst[sl_doff[k]] = 0.0;
+        } else if (sl_kind[k] == 3) {
+          if (J < ncols) cp_async8_d(dst + sl_doff[k], Wg + (size_t)J * 64 + sl_src[k]);
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
