@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
 //     fp64 atomics, with Bii / vi pre-summed over the positions (they all hit the same pose block).
 // =================================================================================================
 constexpr int kE2PosBlock = 32;                 // positions per block (constants / per-position sums staged per block)
-constexpr int kE2Slice = 2;                     // positions per cp.async slice
+constexpr int kE2Slice = 4;                     // positions per cp.async slice
 constexpr int kE2RedStride = 36;                // floats per row of the transpose buffer (conflict-free both ways)
 constexpr int kE2AccStride = 28;
 constexpr int kE2ArrF2 = 32 * (kE2Slice + 1);                       // float2 per staged array: [track][slice + 1]
@@ -502,14 +502,27 @@ __global__ void __launch_bounds__(kE2Threads, 3) k_edge_pass_v2(PlanView pv, Cal
           C += wz0 * et.Jz0 + wz1 * et.Jz1;                        // ba.py:287
           w += wz0 * et.r0 + wz1 * et.r1;                          // ba.py:292
           if (!STRUCT_ONLY) {
+            // Jj0[1] and Jj1[0] are structural zeros (projective_ops.py:83-95): entries that involve component 0 /
+            // component 1 have one term only, Bjj(1,0) vanishes (adding the exact zero the reference adds)
             float Ej[6], Ei[6];
+            {
+              const float wa00 = et.w0 * et.Jj0[0], wa11 = et.w1 * et.Jj1[1];   // (w Jj)^T, ba.py:254
+              Ej[0] = wa00 * et.Jz0; Ej[1] = wa11 * et.Jz1;                     // Ejk, ba.py:263
+              red[21 * kE2RedStride + lane] = wa00 * et.r0;                     // vj, ba.py:266
+              red[22 * kE2RedStride + lane] = wa11 * et.r1;
+              red[tri(0, 0) * kE2RedStride + lane] = wa00 * et.Jj0[0];          // Bjj, ba.py:260
+              red[tri(1, 0) * kE2RedStride + lane] = 0.0f;
+              red[tri(1, 1) * kE2RedStride + lane] = wa11 * et.Jj1[1];
 #pragma unroll
-            for (int a = 0; a < 6; ++a) {
-              const float wa0 = et.w0 * et.Jj0[a], wa1 = et.w1 * et.Jj1[a];     // (w Jj)^T, ba.py:254
-              Ej[a] = wa0 * et.Jz0 + wa1 * et.Jz1;                              // Ejk, ba.py:263
-              red[(21 + a) * kE2RedStride + lane] = wa0 * et.r0 + wa1 * et.r1;  // vj, ba.py:266
+              for (int a = 2; a < 6; ++a) {
+                const float wa0 = et.w0 * et.Jj0[a], wa1 = et.w1 * et.Jj1[a];
+                Ej[a] = fmaf(wa1, et.Jz1, wa0 * et.Jz0);
+                red[(21 + a) * kE2RedStride + lane] = fmaf(wa1, et.r1, wa0 * et.r0);
+                red[tri(a, 0) * kE2RedStride + lane] = wa0 * et.Jj0[0];
+                red[tri(a, 1) * kE2RedStride + lane] = wa1 * et.Jj1[1];
 #pragma unroll
-              for (int b = 0; b <= a; ++b) red[tri(a, b) * kE2RedStride + lane] = wa0 * et.Jj0[b] + wa1 * et.Jj1[b];  // Bjj, :260
+                for (int b = 2; b <= a; ++b) red[tri(a, b) * kE2RedStride + lane] = fmaf(wa1, et.Jj1[b], wa0 * et.Jj0[b]);
+              }
             }
             adjT_apply(pc.R, pc.t, Ej, Ei);                                     // Eik = -A Ejk, ba.py:262
 #pragma unroll
