@@ -105,7 +105,8 @@ struct BaPlan {
   // double-buffered staging / copy streams of ba_step_host[_async] (ba_aux.cu)
   void *host_pipe;
   void (*host_pipe_destroy)(void *);
-  std::vector<void *> owned;           // every cudaMalloc'ed block, for ba_plan_destroy
+  std::vector<void *> owned;           // every pool block of the plan, for ba_plan_destroy
+  cudaStream_t mem_stream;             // stream the plan's allocations are ordered on
   // optional per-stage timing (ba_plan_enable_timing)
   int timing;
   cudaEvent_t ev[BA_N_STAGES + 1];

@@ -1417,7 +1417,7 @@ extern "C" int ba_update(BaPlan *pl, const BaProblem *pb, const float *weights_a
   if (!pl->pp_buf[0]) {
     for (int k = 0; k < 2; ++k) {
       void *q = nullptr;
-      BA_CUDA(cudaMalloc(&q, (np + nq + 8) * sizeof(float)));
+      BA_CUDA(cudaMallocAsync(&q, (np + nq + 8) * sizeof(float), (cudaStream_t)stream));
       pl->owned.push_back(q);
       pl->pp_buf[k] = (float *)q;
     }
