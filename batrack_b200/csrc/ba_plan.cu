@@ -457,7 +457,8 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     // edge pass: about one wave of CTAs (2 resident per SM) — per-CTA set-up and flush are amortised over
     // more tracks; Schur: units of <= 128 tracks. BA_EDGE_TC / BA_SCHUR_TU override for experiments.
     int tc = std::min(256, std::max(8, cdiv(m, sms)));
-    int tu = std::min(256, std::max(16, 16 * cdiv(cdiv(m, 2 * sms), 16)));    // 256-track units measured 4 us faster than 128 at cfg3
+    int tu = std::min(256, std::max(16, 16 * cdiv(cdiv(m, 2 * sms), 16)));
+    if (tu > 128) tu = 256;               // whole 256-track groups: measured 4 us faster than two 128-track units at cfg3
     if (const char *e = getenv("BA_EDGE_TC")) tc = std::max(1, atoi(e));
     if (const char *e = getenv("BA_SCHUR_TU")) tu = std::max(1, atoi(e));
     int *cflag, *cinc;

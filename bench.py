@@ -441,7 +441,7 @@ def main():
     achieved = alg_rank / (edge_ms * 1e-3) / 1e9 if edge_ms > 0 else None
     traffic = None
     try:        # DRAM bytes of the same kernel from the committed ncu --set full capture (N = 1 only)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_edge_pass"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_edge_pass_v2"]
         traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if world == 1 else None
     except Exception:
         pass
@@ -461,7 +461,7 @@ def main():
                 "steps": n_e2e, "note": e2e_note, "serial_value": e2e_serial,
                 "serial_note": "same copies on ONE stream around BA_rgbd_droid (no overlap), per-step events, L2 flushed"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "k_edge_pass (residual + Jacobian + per-track reduction)",
+        "roofline": {"bound": "hbm", "kernel": "k_edge_pass_v2 (residual + Jacobian + per-track reduction, lane per track)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "algorithmic_bytes": alg_rank, "kernel_ms": edge_ms, "peak_source": peak_src},
         "kernels": {k: {"ms": v, "share": v / tot} for k, v in stages.items()},
