@@ -64,6 +64,12 @@ struct PlanView {
   int n_irregular;         // groups that need the generic edge pass
   int dmax_irregular;      // longest track among them
   const int *patch_track;  // [NM] compact track of a patch or -1
+  // streaming Schur -> solve hand-over: small units published in an order that serves both ends of the pose range first
+  const int *o_t0, *o_grp; // [n_ounits+1], [n_ounits]  Schur units of <= 64 tracks
+  const int *o_order;      // [n_ounits] unit run by CTA k
+  int n_ounits;
+  int *o_flag;             // [n_ounits] completion flag of CTA k (epoch of the last call that completed it)
+  const int *top_need, *bot_need;   // [N] see SolveFeed
 };
 
 // Per-call view: problem pointers + the layout of the reduced system for this fixedp.
@@ -107,6 +113,10 @@ struct BaPlan {
   void (*host_pipe_destroy)(void *);
   std::vector<void *> owned;           // every pool block of the plan, for ba_plan_destroy
   cudaStream_t mem_stream;             // stream the plan's allocations are ordered on
+  // streaming Schur -> solve (single-device ba_step): the solve runs on its own stream next to the Schur kernel
+  cudaStream_t solve_stream;
+  cudaEvent_t ev_step_begin, ev_solved;
+  int epoch;
   // optional per-stage timing (ba_plan_enable_timing)
   int timing;
   cudaEvent_t ev[BA_N_STAGES + 1];
@@ -120,7 +130,14 @@ void layout_for(const BaPlan *p, int fixedp, int *n, int *bw, int *ld, int *off,
 constexpr int kMmaMaxBw = 120;        // widest band the 16x16-tile register window of the DMMA solver covers
 size_t solve_mma_smem_bytes(int M);
 size_t solve_mma_scratch_doubles(int M, int bw);
-int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, cudaStream_t s);
+// Streaming mode of the band solver: the Schur kernel runs concurrently and publishes, per unit and in a fixed
+// order, a completion flag (= epoch); top_need[p] / bot_need[p] = number of leading units of that order that must be
+// complete before the rows of every pose <= p / >= p are final. flags == nullptr: S and y are final at launch.
+struct SolveFeed {
+  const int *flags, *top_need, *bot_need;
+  int epoch, n_units, fixedp;
+};
+int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, const SolveFeed &feed, cudaStream_t s);
 }  // namespace ba
 
 #define BA_CUDA(call)                                                         \

@@ -806,13 +806,18 @@ constexpr int kSchurPad = 2;      // floats of padding per staged row: 8-byte lo
 // Stage layout: E entries [rowlen][tile + kSchurPad] (entry-major like global E: the copy is 8-byte cp.async along
 // the tracks, coalesced), then (Q, w) [tile] float2. A thread reads the two tracks (k, k+1) of one entry with one
 // 8-byte load.
-__global__ void __launch_bounds__(kSchurThreads, 2) k_schur(PlanView pv, CallView cv, int tile_tracks) {
+// Streaming mode (flags != nullptr): CTA k runs unit order[k] of the small-unit list and, when all its atomics are
+// visible, stores `epoch` into flags[k] — the band solver runs next to this kernel and reads rows of S / y as soon as
+// the units that feed them are complete (SolveFeed, ba_solve_mma.cu).
+__global__ void __launch_bounds__(kSchurThreads, 2) k_schur(PlanView pv, CallView cv, int tile_tracks, const int *__restrict__ ut0,
+                                                            const int *__restrict__ ugrp, const int *__restrict__ order,
+                                                            int *__restrict__ flags, int epoch) {
   constexpr int NT = kSchurThreads;
   extern __shared__ __align__(16) float smem[];
   const int tau = threadIdx.x;
-  const int u = blockIdx.x;
-  const int g = pv.u_grp[u];
-  const int t0 = pv.u_t0[u], t1 = pv.u_t0[u + 1];
+  const int u = order ? order[blockIdx.x] : blockIdx.x;
+  const int g = ugrp[u];
+  const int t0 = ut0[u], t1 = ut0[u + 1];
   const int gt0 = pv.g_t0[g];
   const int W = pv.g_W[g];
   const int rowlen = 6 * W;
@@ -929,6 +934,11 @@ __global__ void __launch_bounds__(kSchurThreads, 2) k_schur(PlanView pv, CallVie
             if (a != b || e2 <= c) red_add(S_at(cv, ra + c, rb + e2), -acc[c * 6 + e2]);
       }
     }
+  }
+  if (flags) {                                    // release: every thread's atomics first, then the flag
+    __threadfence();
+    __syncthreads();
+    if (tau == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + blockIdx.x), "r"(epoch) : "memory");
   }
 }
 
@@ -1288,7 +1298,17 @@ static int make_call(BaPlan *pl, const BaProblem *pb, CallView *cv) {
 
 using namespace ba;
 
-extern "C" int ba_assemble(BaPlan *pl, const BaProblem *pb, void *stream_) {
+// Can the reduced system of this call go to the DMMA band solver (and therefore be streamed to it)?
+static bool mma_solver_applies(const CallView &cv) {
+  static const char *force = getenv("BA_SOLVER");        // "window" / "dense": force a fallback (tests, A/B timing)
+  const bool want_mma = !force || !force[0] || force[0] == 'm';
+  return want_mma && cv.ld != cv.M && cv.bw <= kMmaMaxBw && solve_mma_smem_bytes(cv.M) <= 227 * 1024 - 64;
+}
+
+// streaming != 0 (single-device ba_step, band solver): after the edge pass the solver is launched on the plan's own
+// stream, then the Schur kernel runs its small units in "both ends first" order and publishes completion flags;
+// the solver eliminates columns while the Schur kernel is still working on the middle of the pose range.
+static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int streaming) {
   CallView cv;
   int rc = make_call(pl, pb, &cv);
   if (rc) return rc;
@@ -1347,11 +1367,22 @@ extern "C" int ba_assemble(BaPlan *pl, const BaProblem *pb, void *stream_) {
       attr_set = true;
     }
     if (smem > 200 * 1024) return BA_ERR_ARG;
-    k_schur<<<pv.n_units, kSchurThreads, smem, s>>>(pv, cv, tile); BA_LAUNCH_CHECK();
+    if (streaming) {
+      SolveFeed feed{pv.o_flag, pv.top_need, pv.bot_need, pl->epoch, pv.n_ounits, pb->fixedp};
+      rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, feed, pl->solve_stream);
+      if (rc) return rc;
+      BA_CUDA(cudaEventRecord(pl->ev_solved, pl->solve_stream));
+      k_schur<<<pv.n_ounits, kSchurThreads, smem, s>>>(pv, cv, tile, pv.o_t0, pv.o_grp, pv.o_order, pv.o_flag, pl->epoch);
+      BA_LAUNCH_CHECK();
+    } else {
+      k_schur<<<pv.n_units, kSchurThreads, smem, s>>>(pv, cv, tile, pv.u_t0, pv.u_grp, nullptr, nullptr, 0); BA_LAUNCH_CHECK();
+    }
   }
   BA_MARK(pl, BA_STAGE_SOLVE, s);      // closes SCHUR; a sharded caller's all-reduce lands in SOLVE's interval
   return BA_OK;
 }
+
+extern "C" int ba_assemble(BaPlan *pl, const BaProblem *pb, void *stream_) { return assemble_impl(pl, pb, stream_, 0); }
 
 extern "C" int ba_plan_reduced_system(const BaPlan *pl, double **ptr, int64_t *n_values) {
   int64_t *n_floats = n_values;
@@ -1363,7 +1394,8 @@ extern "C" int ba_plan_reduced_system(const BaPlan *pl, double **ptr, int64_t *n
   return BA_OK;
 }
 
-extern "C" int ba_solve_update(BaPlan *pl, const BaProblem *pb, void *stream_) {
+// solved != 0: the solve was launched by the streaming assemble; wait for it on the caller's stream
+static int solve_update_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int solved) {
   CallView cv;
   int rc = make_call(pl, pb, &cv);
   if (rc) return rc;
@@ -1371,7 +1403,9 @@ extern "C" int ba_solve_update(BaPlan *pl, const BaProblem *pb, void *stream_) {
   cudaStream_t s = (cudaStream_t)stream_;
   const PlanView &pv = pl->v;
   const bool so = pb->structure_only || cv.n == 0;
-  if (!so) {
+  if (!so && solved) {
+    BA_CUDA(cudaStreamWaitEvent(s, pl->ev_solved, 0));
+  } else if (!so) {
     if (!(pl->ev_mask & (1u << BA_STAGE_SOLVE))) BA_MARK(pl, BA_STAGE_SOLVE, s);
     static bool attr_set = false;
     if (!attr_set) {
@@ -1381,10 +1415,9 @@ extern "C" int ba_solve_update(BaPlan *pl, const BaProblem *pb, void *stream_) {
     }
     const int WS = cv.bw + 1, WSP = WS | 1;
     const size_t smem = ((size_t)WS * WSP + cv.M + WS) * sizeof(double);
-    static const char *force = getenv("BA_SOLVER");        // "window" / "dense": force a fallback (tests, A/B timing)
-    const bool want_mma = !force || !force[0] || force[0] == 'm';
-    if (want_mma && cv.ld != cv.M && cv.bw <= kMmaMaxBw && solve_mma_smem_bytes(cv.M) <= 227 * 1024 - 64) {
-      rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, s);
+    static const char *force = getenv("BA_SOLVER");
+    if (mma_solver_applies(cv)) {
+      rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, SolveFeed{nullptr, nullptr, nullptr, 0, 0, 0}, s);
       if (rc) return rc;
     } else if (cv.ld != cv.M && smem <= 227 * 1024 - 64 && !(force && force[0] == 'd')) {
       k_solve_window<<<1, kSolveThreads, smem, s>>>(cv, pb->monodisp ? 1 : 0); BA_LAUNCH_CHECK();
@@ -1405,8 +1438,32 @@ extern "C" int ba_solve_update(BaPlan *pl, const BaProblem *pb, void *stream_) {
   return BA_OK;
 }
 
+extern "C" int ba_solve_update(BaPlan *pl, const BaProblem *pb, void *stream_) { return solve_update_impl(pl, pb, stream_, 0); }
+
 extern "C" int ba_step(BaPlan *pl, const BaProblem *pb, void *stream) {
-  int rc = ba_assemble(pl, pb, stream);
+  // Streaming hand-over Schur -> solve when the band solver applies (BA_STREAM=0 switches it off)
+  static const int stream_on = getenv("BA_STREAM") ? atoi(getenv("BA_STREAM")) : 1;
+  CallView cv;
+  int rc = make_call(pl, pb, &cv);
+  if (rc) return rc;
+  const bool so = pb->structure_only || cv.n == 0;
+  if (stream_on && !so && pl->v.n_ounits > 0 && mma_solver_applies(cv) && pb->poses_out && pb->patches_out) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!pl->solve_stream) {
+      int lo = 0, hi = 0;
+      BA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      BA_CUDA(cudaStreamCreateWithPriority(&pl->solve_stream, cudaStreamNonBlocking, hi));
+      BA_CUDA(cudaEventCreateWithFlags(&pl->ev_step_begin, cudaEventDisableTiming));
+      BA_CUDA(cudaEventCreateWithFlags(&pl->ev_solved, cudaEventDisableTiming));
+    }
+    pl->epoch += 1;
+    BA_CUDA(cudaEventRecord(pl->ev_step_begin, s));                 // the previous call's back-substitution reads dX
+    BA_CUDA(cudaStreamWaitEvent(pl->solve_stream, pl->ev_step_begin, 0));
+    rc = assemble_impl(pl, pb, stream, 1);
+    if (rc) return rc;
+    return solve_update_impl(pl, pb, stream, 1);
+  }
+  rc = ba_assemble(pl, pb, stream);
   if (rc) return rc;
   return ba_solve_update(pl, pb, stream);
 }

@@ -255,6 +255,30 @@ __global__ void k_group_slots(const int *__restrict__ g_t0, const int *__restric
 
 __global__ void k_zero_last(long long *p, int idx) { p[idx] = 0; }
 
+// Streaming Schur -> solve hand-over. CTA k of the Schur kernel runs unit o_order[k]: units from both ends of the
+// track range alternate, so the rows the two elimination fronts of the solver need first are final first.
+__global__ void k_unit_order(int n, int *__restrict__ order) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) order[k] = (k & 1) ? n - 1 - (k >> 1) : (k >> 1);
+}
+// maxorder[q] = 1 + the last CTA (in launch order) whose unit touches pose q
+__global__ void k_unit_reach(const int *__restrict__ order, const int *__restrict__ o_grp, const int *__restrict__ g_pat,
+                             const int *__restrict__ g_W, const int *__restrict__ slot_pose, int n, int *__restrict__ maxorder) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int g = o_grp[order[k]];
+  const int *sp = slot_pose + 2 * g_pat[g];
+  for (int s = 0; s < g_W[g]; ++s) atomicMax(&maxorder[sp[s]], k + 1);
+}
+// top_need[p] = max over q <= p, bot_need[p] = max over q >= p (one thread: N <= 65535, once per plan)
+__global__ void k_need_prefix(const int *__restrict__ maxorder, int N, int *__restrict__ top_need, int *__restrict__ bot_need) {
+  if (blockIdx.x || threadIdx.x) return;
+  int m = 0;
+  for (int p = 0; p < N; ++p) { m = max(m, maxorder[p]); top_need[p] = m; }
+  m = 0;
+  for (int p = N - 1; p >= 0; --p) { m = max(m, maxorder[p]); bot_need[p] = m; }
+}
+
 // inverse of kx: compact track of a patch, -1 for patches without edges (back-substitution runs per patch)
 __global__ void k_patch_track(const int *__restrict__ kx, int m, int *__restrict__ patch_track) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,6 +402,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
   if (mem_pool_init() != cudaSuccess) return set_cuda_error(cudaGetLastError(), "memory pool");
   BaPlan *pl = new BaPlan();
   pl->mem_stream = s;                      // allocations are ordered on the creation stream (used on it right away)
+  pl->solve_stream = nullptr; pl->ev_step_begin = pl->ev_solved = nullptr; pl->epoch = 0;
   std::memset(&pl->info, 0, sizeof(pl->info));
   std::memset(&pl->v, 0, sizeof(pl->v));
   pl->device = dev;
@@ -471,10 +496,13 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     while (kp < kEdge2Warps && (int64_t)cdiv(m, 32) * kp < 12 * sms && cdiv(hmeta_dmax, kp) > 2) kp *= 2;
     if (const char *e = getenv("BA_EDGE2_KP")) { int v2 = atoi(e); if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8) kp = v2; }
     const int tx = 32 * (kEdge2Warps / kp);
-    int counts[3] = {0, 0, 0};
-    int *unit_t0[3], *unit_grp[3];
-    for (int pass = 0; pass < 3; ++pass) {
-      k_chunk_flags<<<cdiv(m, TB), TB, 0, s>>>(t_grp, g_t0, m, pass == 0 ? tc : (pass == 1 ? tu : tx), cflag); PL_LAUNCH();
+    int counts[4] = {0, 0, 0, 0};
+    int *unit_t0[4], *unit_grp[4];
+    int to = 64;                                       // Schur units of the streaming hand-over to the solver
+    if (const char *e = getenv("BA_STREAM_TU")) to = std::max(16, atoi(e) & ~3);
+    const int unit_len[4] = {tc, tu, tx, to};
+    for (int pass = 0; pass < 4; ++pass) {
+      k_chunk_flags<<<cdiv(m, TB), TB, 0, s>>>(t_grp, g_t0, m, unit_len[pass], cflag); PL_LAUNCH();
       PL_CUDA(inclusive_sum(sc, cflag, cinc, m, s));
       PL_CUDA(cudaMemcpyAsync(&counts[pass], cinc + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
       PL_CUDA(cudaStreamSynchronize(s));
@@ -515,6 +543,19 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     v.g_nm = g_nm; v.ms_ptr = ms_ptr; v.ms_slot = ms_slot; v.pat_ri = pat_ri; v.pat_rj = pat_rj; v.dmax = hmeta[META_DMAX];
     v.c_t0 = unit_t0[0]; v.c_grp = unit_grp[0]; v.u_t0 = unit_t0[1]; v.u_grp = unit_grp[1];
     v.x_t0 = unit_t0[2]; v.x_grp = unit_grp[2]; v.n_xchunks = counts[2]; v.e2_kp = kp;
+    {
+      int *order, *flag, *maxo, *tneed, *bneed;
+      const int no = counts[3];
+      PL_CUDA(own(pl, &order, no)); PL_CUDA(own(pl, &flag, no)); PL_CUDA(own(pl, &tneed, N)); PL_CUDA(own(pl, &bneed, N));
+      PL_CUDA(sc.get(&maxo, N));
+      PL_CUDA(cudaMemsetAsync(flag, 0, (size_t)no * sizeof(int), s));
+      PL_CUDA(cudaMemsetAsync(maxo, 0, (size_t)N * sizeof(int), s));
+      k_unit_order<<<cdiv(no, TB), TB, 0, s>>>(no, order); PL_LAUNCH();
+      k_unit_reach<<<cdiv(no, TB), TB, 0, s>>>(order, unit_grp[3], g_pat, g_W, slot_pose, no, maxo); PL_LAUNCH();
+      k_need_prefix<<<1, 32, 0, s>>>(maxo, N, tneed, bneed); PL_LAUNCH();
+      v.o_t0 = unit_t0[3]; v.o_grp = unit_grp[3]; v.o_order = order; v.n_ounits = no; v.o_flag = flag;
+      v.top_need = tneed; v.bot_need = bneed;
+    }
     v.pat_ps = pat_ps; v.g_reg = g_reg; v.n_irregular = hmeta[META_NIRREG]; v.dmax_irregular = hmeta[META_DMAX_IRREG];
     {
       int *ptk;
@@ -560,6 +601,9 @@ extern "C" void ba_plan_destroy(BaPlan *pl) {
   // then hand the blocks back to the pool
   cudaDeviceSynchronize();
   for (void *p : pl->owned) cudaFreeAsync(p, g_mem_stream);
+  if (pl->solve_stream) cudaStreamDestroy(pl->solve_stream);
+  if (pl->ev_step_begin) cudaEventDestroy(pl->ev_step_begin);
+  if (pl->ev_solved) cudaEventDestroy(pl->ev_solved);
   if (pl->host_pipe && pl->host_pipe_destroy) pl->host_pipe_destroy(pl->host_pipe);
   for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
   delete pl;
