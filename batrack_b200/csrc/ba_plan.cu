@@ -109,11 +109,14 @@ __global__ void k_fill_groups(const int *__restrict__ gflag, const int *__restri
 }
 
 // Work units = a group's tracks split into the fewest equal pieces of at most `tc` consecutive tracks.
+// Groups g_lo <= g < g_hi use units of at most tc_mid tracks instead (streaming Schur units: small at both ends of
+// the pose range, where the solver starts, large in the middle).
 __global__ void k_chunk_flags(const int *__restrict__ t_grp, const int *__restrict__ g_t0, int m, int tc,
-                              int *__restrict__ cflag) {
+                              int *__restrict__ cflag, int g_lo = 0, int g_hi = 0, int tc_mid = 0) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m) return;
   const int g = t_grp[t];
+  if (g >= g_lo && g < g_hi) tc = tc_mid;
   const int T = g_t0[g + 1] - g_t0[g];
   const int pieces = (T + tc - 1) / tc;
   const int len = ((T + pieces - 1) / pieces + 3) & ~3;          // multiple of 4: 16-byte aligned starts in the E rows
@@ -502,7 +505,14 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     if (const char *e = getenv("BA_STREAM_TU")) to = std::max(16, atoi(e) & ~3);
     const int unit_len[4] = {tc, tu, tx, to};
     for (int pass = 0; pass < 4; ++pass) {
-      k_chunk_flags<<<cdiv(m, TB), TB, 0, s>>>(t_grp, g_t0, m, unit_len[pass], cflag); PL_LAUNCH();
+      if (pass == 3) {                                 // optionally large units in the middle of the pose range (measured at
+        int gend = 1 << 30;                            // 256 KF: 24 / 40 / 64 end groups small: 525 / 517 / 492 us, all small 494)
+        if (const char *e = getenv("BA_STREAM_GEND")) gend = std::max(0, atoi(e));
+        k_chunk_flags<<<cdiv(m, TB), TB, 0, s>>>(t_grp, g_t0, m, unit_len[pass], cflag, std::min(gend, G), G - std::min(gend, G), 256);
+      } else {
+        k_chunk_flags<<<cdiv(m, TB), TB, 0, s>>>(t_grp, g_t0, m, unit_len[pass], cflag);
+      }
+      PL_LAUNCH();
       PL_CUDA(inclusive_sum(sc, cflag, cinc, m, s));
       PL_CUDA(cudaMemcpyAsync(&counts[pass], cinc + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
       PL_CUDA(cudaStreamSynchronize(s));
