@@ -1372,7 +1372,8 @@ static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int str
       rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, feed, pl->solve_stream);
       if (rc) return rc;
       BA_CUDA(cudaEventRecord(pl->ev_solved, pl->solve_stream));
-      k_schur<<<pv.n_ounits, kSchurThreads, smem, s>>>(pv, cv, tile, pv.o_t0, pv.o_grp, pv.o_order, pv.o_flag, pl->epoch);
+      static const size_t stream_smem = getenv("BA_STREAM_SMEM_KB") ? (size_t)atoi(getenv("BA_STREAM_SMEM_KB")) * 1024 : 0;   // experiment: throttle occupancy
+      k_schur<<<pv.n_ounits, kSchurThreads, std::max(smem, stream_smem), s>>>(pv, cv, tile, pv.o_t0, pv.o_grp, pv.o_order, pv.o_flag, pl->epoch);
       BA_LAUNCH_CHECK();
     } else {
       k_schur<<<pv.n_units, kSchurThreads, smem, s>>>(pv, cv, tile, pv.u_t0, pv.u_grp, nullptr, nullptr, 0); BA_LAUNCH_CHECK();
