@@ -133,9 +133,13 @@ size_t solve_mma_scratch_doubles(int M, int bw);
 // Streaming mode of the band solver: the Schur kernel runs concurrently and publishes, per unit and in a fixed
 // order, a completion flag (= epoch); top_need[p] / bot_need[p] = number of leading units of that order that must be
 // complete before the rows of every pose <= p / >= p are final. flags == nullptr: S and y are final at launch.
+// mode 0: plain solve; 1: streaming (writes redo[0] = 1 if it gave up waiting: the producer did not run concurrently,
+// e.g. kernels serialised by a profiler); 2: stand-by launch, does the plain solve only if redo[0] != 0.
 struct SolveFeed {
   const int *flags, *top_need, *bot_need;
   int epoch, n_units, fixedp;
+  int mode;
+  int *redo;
 };
 int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, const SolveFeed &feed, cudaStream_t s);
 }  // namespace ba

@@ -200,6 +200,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         return run_reference(args, rank)
+    if args.profile:
+        # ncu serialises kernels: profile every kernel in its stand-alone form (no Schur / solve overlap)
+        os.environ.setdefault("BA_STREAM", "0")
     if args.warmup < 3:
         args.warmup = 3
 
