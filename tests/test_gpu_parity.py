@@ -377,3 +377,38 @@ def test_host_buffer_pipeline_equals_device_call():
     with pytest.raises(RuntimeError):
         hba.submit(t["poses"], host["patches"], host["patches_monodisp"], host["intrinsics"], host["targets_2d"], ws[0],
                    ps.lmbda, ps.bounds, *outs[0])
+
+
+@pytest.mark.parametrize("n_kf", [64, 112])
+def test_band_solver_failure_is_silent_and_recoverable(n_kf):
+    """The band (DMMA) solver — plain at 64 keyframes, twisted over two CTAs at 112 (>= 64 tile columns) — launched
+    next to the Schur kernel (streaming hand-over): a failed factorisation (ba.py:9-13) leaves the poses unchanged
+    while the depths still move, and the next call on the same plan is correct again (flags carry a new epoch)."""
+    from batrack_b200 import synth
+    from batrack_b200.ba import BA_rgbd_droid
+    from batrack_b200.lietorch import SE3
+    from batrack_b200.plan import Plan
+    from gpu_util import as_cuda
+    prob = synth.make_window_problem(n_kf, 64, 19, seed=3)
+    t = as_cuda(prob)
+    N, NM = t["poses"].shape[1], t["patches"].shape[1]
+    plan = Plan(t["ii"], t["jj"], t["kk"], N, NM)
+    assert plan.info.banded
+    w = torch.from_numpy(prob.weights).cuda()[None]
+
+    def call(ep):
+        return BA_rgbd_droid(SE3(t["poses"]), t["patches"], t["patches_monodisp"], t["intrinsics"], t["targets_2d"], None,
+                             w, prob.lmbda, t["ii"], t["jj"], t["kk"], prob.bounds, ep=ep, fixedp=prob.fixedp,
+                             loss=prob.loss, alpha=prob.alpha, plan=plan)
+
+    G0, p0 = call(prob.ep)
+    assert plan.status() == 0
+    Gf, pf = call(-1e12)                                                  # A = S - 1e12 I is not positive definite
+    assert plan.status() & 1
+    assert rel_err(Gf.data.cpu().numpy(), t["poses"].cpu().numpy()) < 1e-6
+    assert torch.isfinite(pf).all() and not torch.equal(pf, t["patches"])
+    G1, p1 = call(prob.ep)
+    assert plan.status() == 0
+    assert rel_err(G1.data.cpu().numpy(), G0.data.cpu().numpy()) < 1e-6 and rel_err(p1.cpu().numpy(), p0.cpu().numpy()) < 1e-6
+    P64, D64 = _oracle().run_sequence(prob, [prob.weights], [False], torch.float64, mode="sparse")
+    assert rel_err(G0.data[0].cpu().numpy(), P64[0]) < TOL and rel_err(p0[0, :, 2, 0, 0].cpu().numpy(), D64[0]) < TOL
