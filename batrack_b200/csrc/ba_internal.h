@@ -117,6 +117,7 @@ struct BaPlan {
   cudaStream_t solve_stream;
   cudaEvent_t ev_step_begin, ev_solved;
   int epoch;
+  long long solve_shape_key;
   // optional per-stage timing (ba_plan_enable_timing)
   int timing;
   cudaEvent_t ev[BA_N_STAGES + 1];
@@ -140,6 +141,7 @@ struct SolveFeed {
   int epoch, n_units, fixedp;
   int mode;
   int *redo;
+  long long *shape_key;     // host: (M, bw) the solver scratch was last cleared for (plan-owned)
 };
 int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, const SolveFeed &feed, cudaStream_t s);
 }  // namespace ba

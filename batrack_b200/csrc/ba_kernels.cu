@@ -1368,7 +1368,7 @@ static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int str
     }
     if (smem > 200 * 1024) return BA_ERR_ARG;
     if (streaming) {
-      SolveFeed feed{pv.o_flag, pv.top_need, pv.bot_need, pl->epoch, pv.n_ounits, pb->fixedp, 1, pl->status + 2};
+      SolveFeed feed{pv.o_flag, pv.top_need, pv.bot_need, pl->epoch, pv.n_ounits, pb->fixedp, 1, pl->status + 2, &pl->solve_shape_key};
       BA_CUDA(cudaMemsetAsync(pl->status + 2, 0, sizeof(int), pl->solve_stream));
       rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, feed, pl->solve_stream);
       if (rc) return rc;
@@ -1409,7 +1409,7 @@ static int solve_update_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int
     // join the streaming solve; the stand-by launch behind it does the solve only if that one gave up (kernels
     // serialised by a profiler / sanitizer: its producer never ran next to it)
     BA_CUDA(cudaStreamWaitEvent(s, pl->ev_solved, 0));
-    rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, SolveFeed{nullptr, nullptr, nullptr, 0, 0, 0, 2, pl->status + 2}, s);
+    rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, SolveFeed{nullptr, nullptr, nullptr, 0, 0, 0, 2, pl->status + 2, &pl->solve_shape_key}, s);
     if (rc) return rc;
   } else if (!so) {
     if (!(pl->ev_mask & (1u << BA_STAGE_SOLVE))) BA_MARK(pl, BA_STAGE_SOLVE, s);
@@ -1423,7 +1423,7 @@ static int solve_update_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int
     const size_t smem = ((size_t)WS * WSP + cv.M + WS) * sizeof(double);
     static const char *force = getenv("BA_SOLVER");
     if (mma_solver_applies(cv)) {
-      rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, SolveFeed{nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr}, s);
+      rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, SolveFeed{nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, &pl->solve_shape_key}, s);
       if (rc) return rc;
     } else if (cv.ld != cv.M && smem <= 227 * 1024 - 64 && !(force && force[0] == 'd')) {
       k_solve_window<<<1, kSolveThreads, smem, s>>>(cv, pb->monodisp ? 1 : 0); BA_LAUNCH_CHECK();

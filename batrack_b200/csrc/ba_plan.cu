@@ -405,7 +405,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
   if (mem_pool_init() != cudaSuccess) return set_cuda_error(cudaGetLastError(), "memory pool");
   BaPlan *pl = new BaPlan();
   pl->mem_stream = s;                      // allocations are ordered on the creation stream (used on it right away)
-  pl->solve_stream = nullptr; pl->ev_step_begin = pl->ev_solved = nullptr; pl->epoch = 0;
+  pl->solve_stream = nullptr; pl->ev_step_begin = pl->ev_solved = nullptr; pl->epoch = 0; pl->solve_shape_key = -1;
   std::memset(&pl->info, 0, sizeof(pl->info));
   std::memset(&pl->v, 0, sizeof(pl->v));
   pl->device = dev;
