@@ -68,7 +68,7 @@ struct PlanView {
   const int *o_t0, *o_grp; // [n_ounits+1], [n_ounits]  Schur units of <= 64 tracks
   const int *o_order;      // [n_ounits] unit run by CTA k
   int n_ounits;
-  int *o_flag;             // [n_ounits] completion flag of CTA k (epoch of the last call that completed it)
+  int *o_flag;             // unused (the flags live behind y in the reduced-system buffer and are cleared with it)
   const int *top_need, *bot_need;   // [N] see SolveFeed
 };
 
@@ -132,7 +132,7 @@ constexpr int kMmaMaxBw = 120;        // widest band the 16x16-tile register win
 size_t solve_mma_smem_bytes(int M);
 size_t solve_mma_scratch_doubles(int M, int bw);
 // Streaming mode of the band solver: the Schur kernel runs concurrently and publishes, per unit and in a fixed
-// order, a completion flag (= epoch); top_need[p] / bot_need[p] = number of leading units of that order that must be
+// order, a completion flag (= epoch, 1: the flags are cleared with S at the start of the call); top_need[p] / bot_need[p] = number of leading units of that order that must be
 // complete before the rows of every pose <= p / >= p are final. flags == nullptr: S and y are final at launch.
 // mode 0: plain solve; 1: streaming (writes redo[0] = 1 if it gave up waiting: the producer did not run concurrently,
 // e.g. kernels serialised by a profiler); 2: stand-by launch, does the plain solve only if redo[0] != 0.

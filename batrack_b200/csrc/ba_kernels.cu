@@ -807,7 +807,7 @@ constexpr int kSchurPad = 2;      // floats of padding per staged row: 8-byte lo
 // the tracks, coalesced), then (Q, w) [tile] float2. A thread reads the two tracks (k, k+1) of one entry with one
 // 8-byte load.
 // Streaming mode (flags != nullptr): CTA k runs unit order[k] of the small-unit list and, when all its atomics are
-// visible, stores `epoch` into flags[k] — the band solver runs next to this kernel and reads rows of S / y as soon as
+// visible, stores `epoch` (1; the flags are cleared with S at the start of the call) into flags[k] — the band solver runs next to this kernel and reads rows of S / y as soon as
 // the units that feed them are complete (SolveFeed, ba_solve_mma.cu).
 __global__ void __launch_bounds__(kSchurThreads, 2) k_schur(PlanView pv, CallView cv, int tile_tracks, const int *__restrict__ ut0,
                                                             const int *__restrict__ ugrp, const int *__restrict__ order,
@@ -1344,7 +1344,13 @@ static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int str
     if (has_long) { k_edge_pass_long<true><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
   } else {
     BA_MARK(pl, BA_STAGE_ZERO, s);
-    BA_CUDA(cudaMemsetAsync(cv.S, 0, (size_t)((cv.y - cv.S) + cv.M) * sizeof(double), s));
+    // streaming: the completion flags of the Schur units sit right behind y and are cleared by the same memset (no
+    // per-call state on the host: a captured CUDA graph of this call can be replayed)
+    BA_CUDA(cudaMemsetAsync(cv.S, 0, (size_t)((cv.y - cv.S) + cv.M) * sizeof(double) + (streaming ? (size_t)pv.n_ounits * sizeof(int) : 0), s));
+    if (streaming) {
+      BA_CUDA(cudaEventRecord(pl->ev_step_begin, s));               // flags cleared; the previous call's back-substitution (reads dX) is behind
+      BA_CUDA(cudaStreamWaitEvent(pl->solve_stream, pl->ev_step_begin, 0));
+    }
     BA_MARK(pl, BA_STAGE_EDGE, s);
     if (any_regular) { k_edge_pass_v2<false><<<pv.n_xchunks, kE2Threads, edge2_smem_bytes(pv.e2_kp), s>>>(pv, cv); BA_LAUNCH_CHECK(); }
     if (any_irregular) { k_edge_pass<false><<<pv.n_chunks, kEdgeThreads, kEdgeSmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
@@ -1368,13 +1374,14 @@ static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int str
     }
     if (smem > 200 * 1024) return BA_ERR_ARG;
     if (streaming) {
-      SolveFeed feed{pv.o_flag, pv.top_need, pv.bot_need, pl->epoch, pv.n_ounits, pb->fixedp, 1, pl->status + 2, &pl->solve_shape_key};
+      int *flags = reinterpret_cast<int *>(cv.y + cv.M);
+      SolveFeed feed{flags, pv.top_need, pv.bot_need, 1, pv.n_ounits, pb->fixedp, 1, pl->status + 2, &pl->solve_shape_key};
       BA_CUDA(cudaMemsetAsync(pl->status + 2, 0, sizeof(int), pl->solve_stream));
       rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, feed, pl->solve_stream);
       if (rc) return rc;
       BA_CUDA(cudaEventRecord(pl->ev_solved, pl->solve_stream));
       static const size_t stream_smem = getenv("BA_STREAM_SMEM_KB") ? (size_t)atoi(getenv("BA_STREAM_SMEM_KB")) * 1024 : 0;   // experiment: throttle occupancy
-      k_schur<<<pv.n_ounits, kSchurThreads, std::max(smem, stream_smem), s>>>(pv, cv, tile, pv.o_t0, pv.o_grp, pv.o_order, pv.o_flag, pl->epoch);
+      k_schur<<<pv.n_ounits, kSchurThreads, std::max(smem, stream_smem), s>>>(pv, cv, tile, pv.o_t0, pv.o_grp, pv.o_order, flags, 1);
       BA_LAUNCH_CHECK();
     } else {
       k_schur<<<pv.n_units, kSchurThreads, smem, s>>>(pv, cv, tile, pv.u_t0, pv.u_grp, nullptr, nullptr, 0); BA_LAUNCH_CHECK();
@@ -1462,9 +1469,6 @@ extern "C" int ba_step(BaPlan *pl, const BaProblem *pb, void *stream) {
       BA_CUDA(cudaEventCreateWithFlags(&pl->ev_step_begin, cudaEventDisableTiming));
       BA_CUDA(cudaEventCreateWithFlags(&pl->ev_solved, cudaEventDisableTiming));
     }
-    pl->epoch += 1;
-    BA_CUDA(cudaEventRecord(pl->ev_step_begin, s));                 // the previous call's back-substitution reads dX
-    BA_CUDA(cudaStreamWaitEvent(pl->solve_stream, pl->ev_step_begin, 0));
     rc = assemble_impl(pl, pb, stream, 1);
     if (rc) return rc;
     return solve_update_impl(pl, pb, stream, 1);

@@ -376,7 +376,7 @@ static int alloc_workspace(BaPlan *pl) {
   // capacity for the smallest fixedp (0): the reduced system only shrinks as fixedp grows
   int n, bw, ld, off; int64_t sf;
   layout_for(pl, 0, &n, &bw, &ld, &off, &sf);
-  int64_t need = sf + 6 * (int64_t)n + 8;
+  int64_t need = sf + 6 * (int64_t)n + 8 + (pl->v.n_ounits + 1) / 2 + 2;     // [S | y | completion flags of the streaming Schur units]
   if (need > pl->sy_floats) {
     BA_CUDA(own(pl, &pl->SY, need));
     BA_CUDA(own(pl, &pl->L, sf + 8));
