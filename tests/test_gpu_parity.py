@@ -412,3 +412,41 @@ def test_band_solver_failure_is_silent_and_recoverable(n_kf):
     assert rel_err(G1.data.cpu().numpy(), G0.data.cpu().numpy()) < 1e-6 and rel_err(p1.cpu().numpy(), p0.cpu().numpy()) < 1e-6
     P64, D64 = _oracle().run_sequence(prob, [prob.weights], [False], torch.float64, mode="sparse")
     assert rel_err(G0.data[0].cpu().numpy(), P64[0]) < TOL and rel_err(p0[0, :, 2, 0, 0].cpu().numpy(), D64[0]) < TOL
+
+
+def test_ba_step_replays_from_a_cuda_graph():
+    """the step must be graph-capturable. A captured BA_rgbd_droid call (band solver streamed next to the
+    Schur kernel: cross-stream events, no host-side per-call state) is replayed on new weights and matches eager calls."""
+    from batrack_b200 import synth
+    from batrack_b200.ba import BA_rgbd_droid
+    from batrack_b200.lietorch import SE3
+    from batrack_b200.plan import Plan
+    from gpu_util import as_cuda
+    prob = synth.make_window_problem(64, 64, 19, seed=5)
+    t = as_cuda(prob)
+    N, NM = t["poses"].shape[1], t["patches"].shape[1]
+    plan = Plan(t["ii"], t["jj"], t["kk"], N, NM)
+    w = torch.from_numpy(prob.weights).cuda()[None].clone()
+
+    def call():
+        return BA_rgbd_droid(SE3(t["poses"]), t["patches"], t["patches_monodisp"], t["intrinsics"], t["targets_2d"], None,
+                             w, prob.lmbda, t["ii"], t["jj"], t["kk"], prob.bounds, ep=prob.ep, fixedp=prob.fixedp,
+                             loss=prob.loss, alpha=prob.alpha, plan=plan)
+
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):                                         # warm-up on the capture stream (streams / events / tables)
+        for _ in range(2):
+            call()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        G, p = call()
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        w.copy_(torch.from_numpy((prob.weights * rng.uniform(0.3, 1.0, prob.weights.shape)).astype(np.float32)).cuda()[None])
+        g.replay()
+        torch.cuda.synchronize()
+        Gr, pr = G.data.clone(), p.clone()
+        Ge, pe = call()
+        assert rel_err(Gr.cpu().numpy(), Ge.data.cpu().numpy()) < 1e-6
+        assert rel_err(pr.cpu().numpy(), pe.cpu().numpy()) < 1e-6
