@@ -103,7 +103,12 @@ int ba_plan_tracks(const BaPlan *plan, int32_t *kx_out /* device, m ints */, voi
 
 /* ---- the iteration ------------------------------------------------------------------------- */
 
-/* One full BA call on one device: assemble -> Schur -> solve -> back-substitute -> retract. */
+/* One full BA call on one device: assemble -> Schur -> solve -> back-substitute -> retract.
+ * Everything is enqueued on `stream` and ordered with it; no host synchronisation. When the reduced system goes to
+ * the band solver, the solver runs on a plan-owned high-priority stream next to the Schur kernel (event-ordered with
+ * `stream` on both sides; DESIGN.md §4 "Streaming hand-over"); the call keeps no per-call state on the host, so it
+ * may be captured into a CUDA graph (after one warm-up call on the capture stream) and replayed. One plan = one call
+ * in flight: calls on the same plan must be issued on one stream (they share the workspace). */
 int ba_step(BaPlan *plan, const BaProblem *prob, void *stream);
 
 /* The BA driver loop of BATRACK.update (main/batrack.py:869-875) in one call: `iters` times
