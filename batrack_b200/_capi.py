@@ -8,6 +8,10 @@ _lib = None
 
 STAGES = ("zero", "edge_pass", "track_q", "schur", "solve", "backsub", "pose_retr")   # BA_STAGE_*
 LOSS_IDS = {"trivial": 0, "huber": 1, "cauchy": 2}      # compute_kernel_weight, ba.py:81-100
+# BA_OPT_* keys of include/batrack_ba.h
+OPTIONS = {"solver": 1, "stream": 2, "stream_smem_kb": 3, "schur_tile": 4, "twist_min": 5, "spin_cap": 6,
+           "solver_trace": 7, "schur": 8}
+SOLVERS = {"diag": 0, "mma": 1, "window": 2, "dense": 3}
 
 
 class BaPlanInfo(C.Structure):
@@ -34,6 +38,9 @@ SYMBOLS = {
     "ba_plan_destroy": (None, [_P]),
     "ba_plan_info": (C.c_int, [_P, C.POINTER(BaPlanInfo)]),
     "ba_plan_set_layout": (C.c_int, [_P, _I32, _I32]),
+    "ba_plan_set_option": (C.c_int, [_P, _I32, _I32]),
+    "ba_plan_get_option": (C.c_int, [_P, _I32, C.POINTER(_I32)]),
+    "ba_plan_read_trace": (C.c_int, [_P, _P, _I64, _P]),
     "ba_plan_tracks": (C.c_int, [_P, _P, _P]),
     "ba_step": (C.c_int, [_P, C.POINTER(BaProblem), _P]),
     "ba_update": (C.c_int, [_P, C.POINTER(BaProblem), _P, _I32, _P]),

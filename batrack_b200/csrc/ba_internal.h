@@ -94,8 +94,22 @@ struct CallView {
 
 }  // namespace ba
 
+// Per-plan switches (ba_plan_set_option); defaults come from the environment once, at plan creation.
+struct BaOptions {
+  int solver;          // BA_OPT_SOLVER: 0 diagonal-ownership DMMA band solver, 1 legacy circular-ownership DMMA solver, 2 scalar window, 3 dense
+  int stream;          // BA_OPT_STREAM: Schur -> solve streaming hand-over in ba_step
+  int stream_smem_kb;  // BA_OPT_STREAM_SMEM_KB: dynamic shared memory forced on the streamed Schur kernel (occupancy throttle, tests)
+  int schur_tile;      // BA_OPT_SCHUR_TILE: tracks per cp.async stage of the SIMT Schur kernel
+  int twist_min;       // BA_OPT_TWIST_MIN
+  int spin_cap;        // BA_OPT_SPIN_CAP
+  int trace;           // BA_OPT_SOLVER_TRACE
+  int schur;           // BA_OPT_SCHUR: 0 tcgen05 (tensor-core) Schur kernel where it applies, 1 SIMT kernel
+};
+
 struct BaPlan {
   BaPlanInfo info;
+  BaOptions opt;
+  long long *trace_buf;
   ba::PlanView v;
   int n_total_layout, bwb_layout;      // what the reduced-system layout uses (>= the local values)
   int device;
@@ -142,8 +156,32 @@ struct SolveFeed {
   int mode;
   int *redo;
   long long *shape_key;     // host: (M, bw) the solver scratch was last cleared for (plan-owned)
+  int spin_cap;             // give-up bound of the streaming waits (iterations of a 40 ns sleep); 0 = default (~3 ms)
+  int twist_min;            // tile columns from which the two-CTA twisted factorisation is used; 0 = default (64)
+  long long *trace;         // optional per-column clock stamps (BA_OPT_SOLVER_TRACE), device memory owned by the plan
 };
+inline SolveFeed make_feed(const BaPlan *pl, const int *flags, const int *top_need, const int *bot_need, int epoch, int n_units,
+                           int fixedp, int mode, int *redo);
 int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, const SolveFeed &feed, cudaStream_t s);
+// diagonal-ownership band solver (ba_solve_diag.cu): same contract, the default
+int launch_solve_band_diag(const CallView &cv, int allow_retry, double *scratch, const SolveFeed &feed, cudaStream_t s);
+size_t solve_diag_smem_bytes(int M);
+// per-device one-time setup (function attributes, static tables); called from ba_plan_create under a lock
+int solve_diag_prepare_device();
+int solve_mma_prepare_device(int dev, cudaStream_t s);
+int kernels_prepare_device();
+int schur_tc_prepare_device();
+}  // namespace ba
+
+namespace ba {
+inline SolveFeed make_feed(const BaPlan *pl, const int *flags, const int *top_need, const int *bot_need, int epoch, int n_units,
+                           int fixedp, int mode, int *redo) {
+  SolveFeed f;
+  f.flags = flags; f.top_need = top_need; f.bot_need = bot_need; f.epoch = epoch; f.n_units = n_units; f.fixedp = fixedp;
+  f.mode = mode; f.redo = redo; f.shape_key = const_cast<long long *>(&pl->solve_shape_key);
+  f.spin_cap = pl->opt.spin_cap; f.twist_min = pl->opt.twist_min; f.trace = pl->opt.trace ? pl->trace_buf : nullptr;
+  return f;
+}
 }  // namespace ba
 
 #define BA_CUDA(call)                                                         \

@@ -1299,11 +1299,28 @@ static int make_call(BaPlan *pl, const BaProblem *pb, CallView *cv) {
 using namespace ba;
 
 // Can the reduced system of this call go to the DMMA band solver (and therefore be streamed to it)?
-static bool mma_solver_applies(const CallView &cv) {
-  static const char *force = getenv("BA_SOLVER");        // "window" / "dense": force a fallback (tests, A/B timing)
-  const bool want_mma = !force || !force[0] || force[0] == 'm';
+static bool mma_solver_applies(const BaPlan *pl, const CallView &cv) {
+  const bool want_mma = pl->opt.solver == 0 || pl->opt.solver == 1;      // BA_OPT_SOLVER 2 / 3 force a fallback (tests, A/B timing)
   return want_mma && cv.ld != cv.M && cv.bw <= kMmaMaxBw && solve_mma_smem_bytes(cv.M) <= 227 * 1024 - 64;
 }
+static int launch_band_solver(const BaPlan *pl, const CallView &cv, int allow_retry, const SolveFeed &feed, cudaStream_t s) {
+  return pl->opt.solver == 1 ? launch_solve_band_mma(cv, allow_retry, pl->Wg, feed, s) : launch_solve_band_diag(cv, allow_retry, pl->Wg, feed, s);
+}
+
+// Function attributes are per device: set for every kernel of this translation unit when a plan is created on a
+// device for the first time (ba_plan.cu), never on the hot path.
+namespace ba {
+int kernels_prepare_device() {
+  BA_CUDA(cudaFuncSetAttribute(k_edge_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
+  BA_CUDA(cudaFuncSetAttribute(k_edge_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
+  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1)));
+  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1)));
+  BA_CUDA(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  BA_CUDA(cudaFuncSetAttribute(k_solve_window, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
+  BA_CUDA(cudaFuncSetAttribute(k_solve_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
+  return BA_OK;
+}
+}  // namespace ba
 
 // streaming != 0 (single-device ba_step, band solver): after the edge pass the solver is launched on the plan's own
 // stream, then the Schur kernel runs its small units in "both ends first" order and publishes completion flags;
@@ -1317,18 +1334,6 @@ static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int str
   const bool so = pb->structure_only || cv.n == 0;                 // ba.py:316
   pl->last_n = cv.n; pl->last_fixedp = pb->fixedp;
   pl->ev_mask = 0;
-  static bool edge_attr_set = false;
-  if (!edge_attr_set) {
-    BA_CUDA(cudaFuncSetAttribute(k_edge_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
-    BA_CUDA(cudaFuncSetAttribute(k_edge_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
-    edge_attr_set = true;
-  }
-  static bool edge2_attr_set = false;
-  if (!edge2_attr_set) {
-    BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1)));
-    BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1)));
-    edge2_attr_set = true;
-  }
   // regular groups (every SLAM graph): lane-per-track kernel; irregular groups: the generic kernels (each kernel
   // returns at once on the groups of the other kind)
   const bool any_regular = pv.n_irregular < pv.G, any_irregular = pv.n_irregular > 0;
@@ -1363,24 +1368,18 @@ static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int str
   BA_MARK(pl, BA_STAGE_SCHUR, s);
   if (!so) {
     const int rowmax = 6 * pl->info.max_slots;
-    int tile = 64;                                                       // per stage; kSchurStages stages in flight; 2 CTAs per SM
-    if (const char *e = getenv("BA_SCHUR_TILE")) tile = std::max(4, atoi(e) & ~3);
+    int tile = std::max(4, pl->opt.schur_tile & ~3);                     // per stage; kSchurStages stages in flight; 2 CTAs per SM
     while (tile > 4 && (size_t)kSchurStages * (rowmax * (tile + kSchurPad) + 2 * tile) * sizeof(float) > 100 * 1024) tile -= 4;
     const size_t smem = (size_t)kSchurStages * (rowmax * (tile + kSchurPad) + 2 * tile) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      BA_CUDA(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
     if (smem > 200 * 1024) return BA_ERR_ARG;
     if (streaming) {
       int *flags = reinterpret_cast<int *>(cv.y + cv.M);
-      SolveFeed feed{flags, pv.top_need, pv.bot_need, 1, pv.n_ounits, pb->fixedp, 1, pl->status + 2, &pl->solve_shape_key};
+      const SolveFeed feed = make_feed(pl, flags, pv.top_need, pv.bot_need, 1, pv.n_ounits, pb->fixedp, 1, pl->status + 2);
       BA_CUDA(cudaMemsetAsync(pl->status + 2, 0, sizeof(int), pl->solve_stream));
-      rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, feed, pl->solve_stream);
+      rc = launch_band_solver(pl, cv, pb->monodisp ? 1 : 0, feed, pl->solve_stream);
       if (rc) return rc;
       BA_CUDA(cudaEventRecord(pl->ev_solved, pl->solve_stream));
-      static const size_t stream_smem = getenv("BA_STREAM_SMEM_KB") ? (size_t)atoi(getenv("BA_STREAM_SMEM_KB")) * 1024 : 0;   // experiment: throttle occupancy
+      const size_t stream_smem = (size_t)pl->opt.stream_smem_kb * 1024;   // BA_OPT_STREAM_SMEM_KB: throttle occupancy (tests force the give-up path with it)
       k_schur<<<pv.n_ounits, kSchurThreads, std::max(smem, stream_smem), s>>>(pv, cv, tile, pv.o_t0, pv.o_grp, pv.o_order, flags, 1);
       BA_LAUNCH_CHECK();
     } else {
@@ -1416,23 +1415,16 @@ static int solve_update_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int
     // join the streaming solve; the stand-by launch behind it does the solve only if that one gave up (kernels
     // serialised by a profiler / sanitizer: its producer never ran next to it)
     BA_CUDA(cudaStreamWaitEvent(s, pl->ev_solved, 0));
-    rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, SolveFeed{nullptr, nullptr, nullptr, 0, 0, 0, 2, pl->status + 2, &pl->solve_shape_key}, s);
+    rc = launch_band_solver(pl, cv, pb->monodisp ? 1 : 0, make_feed(pl, nullptr, nullptr, nullptr, 0, 0, 0, 2, pl->status + 2), s);
     if (rc) return rc;
   } else if (!so) {
     if (!(pl->ev_mask & (1u << BA_STAGE_SOLVE))) BA_MARK(pl, BA_STAGE_SOLVE, s);
-    static bool attr_set = false;
-    if (!attr_set) {
-      BA_CUDA(cudaFuncSetAttribute(k_solve_window, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
-      BA_CUDA(cudaFuncSetAttribute(k_solve_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
-      attr_set = true;
-    }
     const int WS = cv.bw + 1, WSP = WS | 1;
     const size_t smem = ((size_t)WS * WSP + cv.M + WS) * sizeof(double);
-    static const char *force = getenv("BA_SOLVER");
-    if (mma_solver_applies(cv)) {
-      rc = launch_solve_band_mma(cv, pb->monodisp ? 1 : 0, pl->Wg, SolveFeed{nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, &pl->solve_shape_key}, s);
+    if (mma_solver_applies(pl, cv)) {
+      rc = launch_band_solver(pl, cv, pb->monodisp ? 1 : 0, make_feed(pl, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr), s);
       if (rc) return rc;
-    } else if (cv.ld != cv.M && smem <= 227 * 1024 - 64 && !(force && force[0] == 'd')) {
+    } else if (cv.ld != cv.M && smem <= 227 * 1024 - 64 && pl->opt.solver != 3) {
       k_solve_window<<<1, kSolveThreads, smem, s>>>(cv, pb->monodisp ? 1 : 0); BA_LAUNCH_CHECK();
     } else {
       const size_t smem_d = 2 * (size_t)cv.M * sizeof(double);
@@ -1455,12 +1447,12 @@ extern "C" int ba_solve_update(BaPlan *pl, const BaProblem *pb, void *stream_) {
 
 extern "C" int ba_step(BaPlan *pl, const BaProblem *pb, void *stream) {
   // Streaming hand-over Schur -> solve when the band solver applies (BA_STREAM=0 switches it off)
-  static const int stream_on = getenv("BA_STREAM") ? atoi(getenv("BA_STREAM")) : 1;
+  const int stream_on = pl ? pl->opt.stream : 0;
   CallView cv;
   int rc = make_call(pl, pb, &cv);
   if (rc) return rc;
   const bool so = pb->structure_only || cv.n == 0;
-  if (stream_on && !so && pl->v.n_ounits > 0 && mma_solver_applies(cv) && pb->poses_out && pb->patches_out) {
+  if (stream_on && !so && pl->v.n_ounits > 0 && mma_solver_applies(pl, cv) && pb->poses_out && pb->patches_out) {
     cudaStream_t s = (cudaStream_t)stream;
     if (!pl->solve_stream) {
       int lo = 0, hi = 0;

@@ -317,19 +317,54 @@ struct Scratch {
 // Plan-owned memory comes from the device's stream-ordered pool with the release threshold lifted: a SLAM
 // front end rebuilds the plan whenever the graph changes (every frame), and after the first few plans every
 // allocation is a pool hit instead of a cudaMalloc (~40 of them per plan; measured in tools/plan_build_time.py).
-static cudaStream_t g_mem_stream = nullptr;
-static cudaError_t mem_pool_init() {
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lk(mu);
-  if (g_mem_stream) return cudaSuccess;
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
+// All process-wide state is per device: the stream plan memory is released on, and the "attributes set / tables
+// built" flag (function attributes and allocations belong to one device).
+constexpr int kMaxDevices = 64;
+static cudaStream_t g_mem_stream[kMaxDevices] = {nullptr};
+static bool g_dev_ready[kMaxDevices] = {false};
+static std::mutex g_dev_mu;
+static cudaError_t mem_pool_init(int dev) {
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (g_mem_stream[dev]) return cudaSuccess;
+  cudaError_t e;
   cudaMemPool_t pool;
   if ((e = cudaDeviceGetDefaultMemPool(&pool, dev)) != cudaSuccess) return e;
   unsigned long long thr = ~0ull;
   if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr)) != cudaSuccess) return e;
-  return cudaStreamCreateWithFlags(&g_mem_stream, cudaStreamNonBlocking);
+  return cudaStreamCreateWithFlags(&g_mem_stream[dev], cudaStreamNonBlocking);
+}
+// First plan on a device: opt every kernel in to its dynamic shared memory, build the legacy solver's step tables
+// (synchronously, so that no later stream races with the build and nothing is allocated under graph capture).
+static int prepare_device(int dev, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (dev < 0 || dev >= kMaxDevices) return BA_ERR_ARG;
+  if (g_dev_ready[dev]) return BA_OK;
+  int rc = kernels_prepare_device();
+  if (!rc) rc = solve_diag_prepare_device();
+  if (!rc) rc = solve_mma_prepare_device(dev, s);
+  if (!rc) rc = schur_tc_prepare_device();
+  if (!rc) g_dev_ready[dev] = true;
+  return rc;
+}
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+static void options_from_env(BaOptions *o) {
+  o->solver = 0;
+  if (const char *e = getenv("BA_SOLVER")) {               // "diag" / "mma" / "window" / "dense" or 0..3
+    if (e[0] == 'm' || e[0] == '1') o->solver = 1;
+    else if (e[0] == 'w' || e[0] == '2') o->solver = 2;
+    else if ((e[0] == 'd' && e[1] == 'e') || e[0] == '3') o->solver = 3;
+  }
+  o->stream = env_int("BA_STREAM", 1) ? 1 : 0;
+  o->stream_smem_kb = std::max(0, env_int("BA_STREAM_SMEM_KB", 0));
+  o->schur_tile = std::max(4, env_int("BA_SCHUR_TILE", 64));
+  o->twist_min = std::max(17, env_int("BA_TWIST_MIN", 64));
+  o->spin_cap = std::max(0, env_int("BA_SPIN_CAP", 0));
+  o->trace = env_int("BA_SOLVER_TRACE", 0) ? 1 : 0;
+  o->schur = env_int("BA_SCHUR", 0) ? 1 : 0;
 }
 template <typename T> static cudaError_t own(BaPlan *pl, T **p, size_t n) {
   void *q = nullptr;
@@ -402,8 +437,16 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
   int dev = 0;
   BA_CUDA(cudaGetDevice(&dev));
 
-  if (mem_pool_init() != cudaSuccess) return set_cuda_error(cudaGetLastError(), "memory pool");
+  if (mem_pool_init(dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), "memory pool");
+  {
+    const int rc = prepare_device(dev, s);
+    if (rc) return rc;
+  }
   BaPlan *pl = new BaPlan();
+  options_from_env(&pl->opt);
+  pl->trace_buf = nullptr;
+  const int want_trace = pl->opt.trace;
+  pl->opt.trace = 0;
   pl->mem_stream = s;                      // allocations are ordered on the creation stream (used on it right away)
   pl->solve_stream = nullptr; pl->ev_step_begin = pl->ev_solved = nullptr; pl->epoch = 0; pl->solve_shape_key = -1;
   std::memset(&pl->info, 0, sizeof(pl->info));
@@ -421,6 +464,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
   pl->timing = 0;
   pl->ev_mask = 0;
   for (auto &e : pl->ev) e = nullptr;
+  if (want_trace) ba_plan_set_option(pl, BA_OPT_SOLVER_TRACE, 1);
 
   auto fail = [&](int code) { ba_plan_destroy(pl); return code; };
 #define PL_CUDA(call)                                                                      \
@@ -609,14 +653,67 @@ extern "C" void ba_plan_destroy(BaPlan *pl) {
   if (!pl) return;
   // kernels of the last calls may still be running on the caller's streams: wait (what cudaFree did implicitly),
   // then hand the blocks back to the pool
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != pl->device) cudaSetDevice(pl->device);        // the plan's memory, streams and events live on its device
   cudaDeviceSynchronize();
-  for (void *p : pl->owned) cudaFreeAsync(p, g_mem_stream);
+  for (void *p : pl->owned) cudaFreeAsync(p, g_mem_stream[pl->device]);
+  if (pl->trace_buf) cudaFree(pl->trace_buf);
   if (pl->solve_stream) cudaStreamDestroy(pl->solve_stream);
   if (pl->ev_step_begin) cudaEventDestroy(pl->ev_step_begin);
   if (pl->ev_solved) cudaEventDestroy(pl->ev_solved);
   if (pl->host_pipe && pl->host_pipe_destroy) pl->host_pipe_destroy(pl->host_pipe);
   for (auto &e : pl->ev) if (e) cudaEventDestroy(e);
+  if (cur != pl->device) cudaSetDevice(cur);
   delete pl;
+}
+
+constexpr size_t kTraceValues = 16 * 4096 + 32;
+
+extern "C" int ba_plan_set_option(BaPlan *pl, int32_t key, int32_t value) {
+  if (!pl) return BA_ERR_ARG;
+  switch (key) {
+    case BA_OPT_SOLVER: if (value < 0 || value > 3) return BA_ERR_ARG; pl->opt.solver = value; break;
+    case BA_OPT_STREAM: pl->opt.stream = value ? 1 : 0; break;
+    case BA_OPT_STREAM_SMEM_KB: if (value < 0 || value > 200) return BA_ERR_ARG; pl->opt.stream_smem_kb = value; break;
+    case BA_OPT_SCHUR_TILE: if (value < 4) return BA_ERR_ARG; pl->opt.schur_tile = value & ~3; break;
+    case BA_OPT_TWIST_MIN: if (value < 17) return BA_ERR_ARG; pl->opt.twist_min = value; break;
+    case BA_OPT_SPIN_CAP: if (value < 0) return BA_ERR_ARG; pl->opt.spin_cap = value; break;
+    case BA_OPT_SOLVER_TRACE:
+      if (value && !pl->trace_buf) {
+        BA_CUDA(cudaMalloc(&pl->trace_buf, kTraceValues * sizeof(long long)));
+        BA_CUDA(cudaMemset(pl->trace_buf, 0, kTraceValues * sizeof(long long)));
+      }
+      pl->opt.trace = value ? 1 : 0;
+      break;
+    case BA_OPT_SCHUR: if (value < 0 || value > 1) return BA_ERR_ARG; pl->opt.schur = value; break;
+    default: return BA_ERR_ARG;
+  }
+  return BA_OK;
+}
+
+extern "C" int ba_plan_get_option(const BaPlan *pl, int32_t key, int32_t *value) {
+  if (!pl || !value) return BA_ERR_ARG;
+  switch (key) {
+    case BA_OPT_SOLVER: *value = pl->opt.solver; break;
+    case BA_OPT_STREAM: *value = pl->opt.stream; break;
+    case BA_OPT_STREAM_SMEM_KB: *value = pl->opt.stream_smem_kb; break;
+    case BA_OPT_SCHUR_TILE: *value = pl->opt.schur_tile; break;
+    case BA_OPT_TWIST_MIN: *value = pl->opt.twist_min; break;
+    case BA_OPT_SPIN_CAP: *value = pl->opt.spin_cap; break;
+    case BA_OPT_SOLVER_TRACE: *value = pl->opt.trace; break;
+    case BA_OPT_SCHUR: *value = pl->opt.schur; break;
+    default: return BA_ERR_ARG;
+  }
+  return BA_OK;
+}
+
+extern "C" int ba_plan_read_trace(const BaPlan *pl, int64_t *out, int64_t n, void *stream) {
+  if (!pl || !out || n <= 0 || !pl->trace_buf) return BA_ERR_ARG;
+  BA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  BA_CUDA(cudaDeviceSynchronize());
+  BA_CUDA(cudaMemcpy(out, pl->trace_buf, (size_t)std::min<int64_t>(n, (int64_t)kTraceValues) * sizeof(long long), cudaMemcpyDeviceToHost));
+  return BA_OK;
 }
 
 extern "C" int ba_plan_info(const BaPlan *pl, BaPlanInfo *out) {

@@ -45,6 +45,26 @@ class Plan:
         _capi.check(_capi.lib().ba_plan_tracks(self.handle, _capi.ptr(out), _capi.stream_ptr(self.device)))
         return out
 
+    def set_option(self, name, value):
+        """Per-plan switch (BA_OPT_* in include/batrack_ba.h): solver, stream, stream_smem_kb, schur_tile, twist_min,
+        spin_cap, solver_trace, schur. `solver` also takes "diag" / "mma" / "window" / "dense"."""
+        if name == "solver" and isinstance(value, str):
+            value = _capi.SOLVERS[value]
+        _capi.check(_capi.lib().ba_plan_set_option(self.handle, _capi.OPTIONS[name], int(value)), f"set_option({name})")
+
+    def get_option(self, name):
+        v = C.c_int32()
+        _capi.check(_capi.lib().ba_plan_get_option(self.handle, _capi.OPTIONS[name], C.byref(v)), f"get_option({name})")
+        return int(v.value)
+
+    def read_trace(self):
+        """int64 clock stamps of the last traced band solve: [4096 columns][16 slots] + 4 phase stamps per side."""
+        import numpy as np
+        out = np.zeros(16 * 4096 + 32, dtype=np.int64)
+        _capi.check(_capi.lib().ba_plan_read_trace(self.handle, out.ctypes.data_as(C.c_void_p), out.size,
+                                                   _capi.stream_ptr(self.device)), "read_trace")
+        return out
+
     def set_layout(self, n_total, block_bandwidth):
         _capi.check(_capi.lib().ba_plan_set_layout(self.handle, int(n_total), int(block_bandwidth)), "set_layout")
         self.layout_n_total = int(n_total)

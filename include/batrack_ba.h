@@ -97,6 +97,24 @@ int ba_plan_info(const BaPlan *plan, BaPlanInfo *out);
  * rank lays the reduced camera system out identically. Pass the max over ranks. */
 int ba_plan_set_layout(BaPlan *plan, int32_t n_total, int32_t block_bandwidth);
 
+/* Per-plan switches (defaults: the values below, or the environment variable of the same name without the
+ * BA_OPT_ prefix — e.g. BA_SOLVER, BA_STREAM — read once when the plan is created). Returns BA_ERR_ARG for an
+ * unknown key or an unsupported value. None of them changes results beyond summation order. */
+#define BA_OPT_SOLVER 1          /* 0 DMMA band solver, diagonal tile ownership (default); 1 DMMA band solver, circular
+                                    ownership (round-1 kernel); 2 scalar window Cholesky; 3 dense single-CTA Cholesky */
+#define BA_OPT_STREAM 2          /* 1 (default): ba_step starts the band solver next to the Schur kernel */
+#define BA_OPT_STREAM_SMEM_KB 3  /* dynamic shared memory forced on the streamed Schur kernel (occupancy throttle; tests) */
+#define BA_OPT_SCHUR_TILE 4      /* tracks per cp.async stage of the SIMT Schur kernel (default 64) */
+#define BA_OPT_TWIST_MIN 5       /* tile columns (8 unknowns each) from which two CTAs eliminate from both ends (default 64) */
+#define BA_OPT_SPIN_CAP 6        /* give-up bound of the streaming solver's waits, in 40 ns sleeps (default 65536 ~ 3 ms) */
+#define BA_OPT_SOLVER_TRACE 7    /* 1: the band solver records per-column clock stamps (ba_plan_read_trace) */
+#define BA_OPT_SCHUR 8           /* 0 (default): tcgen05 tensor-core Schur kernel where it applies; 1: SIMT kernel */
+int ba_plan_set_option(BaPlan *plan, int32_t key, int32_t value);
+int ba_plan_get_option(const BaPlan *plan, int32_t key, int32_t *value);
+/* Copies the solver trace of the last traced solve to the host: n_values int64 clock stamps
+ * ([column][16 slots] for up to 4096 columns, then 4 phase stamps per side). Synchronises `stream`. */
+int ba_plan_read_trace(const BaPlan *plan, int64_t *out_host, int64_t n_values, void *stream);
+
 /* Device copy-outs for tests and callers that need the compacted indices (ba.py:276): kx[m] int32
  * patch index of every compact track, sorted ascending. */
 int ba_plan_tracks(const BaPlan *plan, int32_t *kx_out /* device, m ints */, void *stream);
