@@ -10,7 +10,7 @@ STAGES = ("zero", "edge_pass", "track_q", "schur", "solve", "backsub", "pose_ret
 LOSS_IDS = {"trivial": 0, "huber": 1, "cauchy": 2}      # compute_kernel_weight, ba.py:81-100
 # BA_OPT_* keys of include/batrack_ba.h
 OPTIONS = {"solver": 1, "stream": 2, "stream_smem_kb": 3, "schur_tile": 4, "twist_min": 5, "spin_cap": 6,
-           "solver_trace": 7, "schur": 8}
+           "solver_trace": 7, "schur": 8, "schur_acc": 9}
 SOLVERS = {"diag": 0, "mma": 1, "window": 2, "dense": 3}
 
 
@@ -53,8 +53,14 @@ SYMBOLS = {
     "ba_plan_last_timing": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "ba_step_host": (C.c_int, [_P, C.POINTER(BaProblem), _P]),
     "ba_step_host_async": (C.c_int, [_P, C.POINTER(BaProblem), _P]),
+    "ba_stage_host_async": (C.c_int, [_P, C.POINTER(BaProblem), C.POINTER(BaProblem), _P]),
+    "ba_unstage_host_async": (C.c_int, [_P, C.POINTER(BaProblem), C.POINTER(BaProblem), _P]),
     "ba_host_sync": (C.c_int, [_P, _P, C.c_int]),
     "ba_reproject": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P]),
+    "ba_transform": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "ba_point_cloud": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P]),
+    "ba_back_proj": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _P, _P]),
+    "ba_proj_to_frames": (C.c_int, [_P, _P, _P, _I32, _I32, _I64, _P, _P]),
     "se3_expm": (C.c_int, [_P, _P, _I64, _P]),
     "se3_logm": (C.c_int, [_P, _P, _I64, _P]),
     "se3_inv": (C.c_int, [_P, _P, _I64, _P]),
@@ -64,6 +70,15 @@ SYMBOLS = {
     "se3_act": (C.c_int, [_P, _P, _P, _I64, _P]),
     "se3_act4": (C.c_int, [_P, _P, _P, _I64, _P]),
     "se3_as_matrix": (C.c_int, [_P, _P, _I64, _P]),
+    "se3d_expm": (C.c_int, [_P, _P, _I64, _P]),
+    "se3d_logm": (C.c_int, [_P, _P, _I64, _P]),
+    "se3d_inv": (C.c_int, [_P, _P, _I64, _P]),
+    "se3d_mul": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "se3d_adj": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "se3d_adjT": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "se3d_act": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "se3d_act4": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "se3d_as_matrix": (C.c_int, [_P, _P, _I64, _P]),
     "ba_error_string": (C.c_char_p, [C.c_int]),
     "ba_last_cuda_error": (C.c_char_p, []),
     "ba_version": (C.c_int, []),
@@ -114,6 +129,20 @@ def ptr(t):
 def stream_ptr(device):
     import torch
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda_float(name, t, contiguous=True):
+    """float32 or float64 CUDA tensor (the SE3 group ops dispatch both, like lietorch/include/dispatch.h:37-45)"""
+    import torch
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: batrack_b200 runs on CUDA tensors only (got {t.device}); there is no CPU fallback")
+    if t.dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"{name}: float32 or float64 required (got {t.dtype})")
+    if contiguous and not t.is_contiguous():
+        raise RuntimeError(f"{name}: input must be contiguous")        # lietorch.cpp:7 CHECK_CONTIGUOUS
+    return t
 
 
 def require_cuda_f32(name, t, contiguous=True):

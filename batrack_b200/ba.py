@@ -77,6 +77,22 @@ def _problem(plan, poses, patches, monodisp, intrinsics, targets, weights, lmbda
     return p, poses_out, patches_out, keep
 
 
+def ensure_sharded_layout(plan, group):
+    """Sharded calls sum the ranks' reduced systems element by element, so every rank must lay [S | y] out
+    for the same number of poses and the same band width, and every rank must take part in the all-reduce: agree on
+    max(n_total), max(block_bandwidth) once per (plan, group). Tracks must be partitioned by rank (each patch's edges on
+    ONE rank): Q = 1 / (C + lambda) is formed from the local C."""
+    if getattr(plan, "_layout_group", None) is group:
+        return
+    import torch.distributed as dist
+    lay = torch.tensor([plan.info.n_total, plan.info.block_bandwidth], device=plan.device, dtype=torch.int64)
+    dist.all_reduce(lay, op=dist.ReduceOp.MAX, group=group)
+    n_total, bwb = int(lay[0]), int(lay[1])
+    if n_total != plan.layout_n_total or bwb != plan.info.block_bandwidth:
+        plan.set_layout(n_total, bwb)
+    plan._layout_group = group
+
+
 def _run(poses, patches, monodisp, intrinsics, targets, weights, lmbda, ii, jj, kk, bounds, ep, PRINT, fixedp,
          structure_only, loss, alpha, group=None, plan=None):
     pdata = poses.data
@@ -89,7 +105,7 @@ def _run(poses, patches, monodisp, intrinsics, targets, weights, lmbda, ii, jj, 
     if PRINT:                                                            # ba.py:244-245
         from . import projective_ops as pops
         coords, v = pops.transform(poses, patches, intrinsics, ii, jj, kk, valid=True)
-        c = coords[..., 0, 0, :]
+        c, v = coords[..., 0, 0, :], v[..., 0, 0]                         # [1,E,2], [1,E] like ba.py:223-226
         r = targets - c
         v = v * (r.norm(dim=-1) < 250).float() * ((c[..., 0] > bounds[0]) & (c[..., 1] > bounds[1]) &
                                                   (c[..., 0] < bounds[2]) & (c[..., 1] < bounds[3])).float()
@@ -101,6 +117,7 @@ def _run(poses, patches, monodisp, intrinsics, targets, weights, lmbda, ii, jj, 
             _capi.check(L.ba_step(plan.handle, C.byref(prob), st), "ba_step")
         else:
             import torch.distributed as dist
+            ensure_sharded_layout(plan, group)
             _capi.check(L.ba_assemble(plan.handle, C.byref(prob), st), "ba_assemble")
             if not structure_only and plan.layout_n_total - int(fixedp) > 0:
                 dist.all_reduce(plan.reduced_system(), op=dist.ReduceOp.SUM, group=group)

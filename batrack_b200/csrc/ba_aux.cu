@@ -5,6 +5,7 @@
 
 #include "ba_internal.h"
 #include "ba_math.cuh"
+#include "se3_t.cuh"
 
 namespace ba {
 
@@ -12,59 +13,60 @@ namespace ba {
 // loads of a warp cover whole 128-byte lines even though each thread's row is 28 bytes.
 enum Se3Op { OP_EXP, OP_LOG, OP_INV, OP_MUL, OP_ADJ, OP_ADJT, OP_ACT, OP_ACT4, OP_MAT };
 
-template <int OP>
-__global__ void k_se3(const float *__restrict__ X, const float *__restrict__ Y, float *__restrict__ out, int64_t B) {
+template <int OP, typename T>
+__global__ void k_se3(const T *__restrict__ X, const T *__restrict__ Y, T *__restrict__ out, int64_t B) {
+  namespace g = se3t;
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= B) return;
   if (OP == OP_EXP) {
-    float a[6];
+    T a[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) a[c] = X[6 * i + c];
-    pose_store(pose_exp(a), out + 7 * i);
+    g::store(g::exp<T>(a), out + 7 * i);
   } else if (OP == OP_LOG) {
-    float a[6];
-    pose_log(pose_load(X + 7 * i), a);
+    T a[6];
+    g::log(g::load(X + 7 * i), a);
 #pragma unroll
     for (int c = 0; c < 6; ++c) out[6 * i + c] = a[c];
   } else if (OP == OP_INV) {
-    pose_store(pose_inv(pose_load(X + 7 * i)), out + 7 * i);
+    g::store(g::inv(g::load(X + 7 * i)), out + 7 * i);
   } else if (OP == OP_MUL) {
-    pose_store(pose_mul(pose_load(X + 7 * i), pose_load(Y + 7 * i)), out + 7 * i);
+    g::store(g::mul(g::load(X + 7 * i), g::load(Y + 7 * i)), out + 7 * i);
   } else if (OP == OP_ADJ || OP == OP_ADJT) {
-    Pose P = pose_load(X + 7 * i);
-    float R[9], a[6], b[6];
-    qmatrix(P.q, R);
+    const g::P<T> Pz = g::load(X + 7 * i);
+    T R[9], a[6], b[6];
+    g::qmatrix(Pz.q, R);
 #pragma unroll
     for (int c = 0; c < 6; ++c) a[c] = Y[6 * i + c];
-    if (OP == OP_ADJ) adj_apply(R, P.t, a, b); else adjT_apply(R, P.t, a, b);
+    if (OP == OP_ADJ) g::adj(R, Pz.t, a, b); else g::adjT(R, Pz.t, a, b);
 #pragma unroll
     for (int c = 0; c < 6; ++c) out[6 * i + c] = b[c];
   } else if (OP == OP_ACT) {
-    Pose P = pose_load(X + 7 * i);
-    Vec3 r = qrotate(P.q, {Y[3 * i], Y[3 * i + 1], Y[3 * i + 2]});
-    out[3 * i] = r.x + P.t.x; out[3 * i + 1] = r.y + P.t.y; out[3 * i + 2] = r.z + P.t.z;
+    const g::P<T> Pz = g::load(X + 7 * i);
+    const g::V<T> r = g::qrotate(Pz.q, g::V<T>{Y[3 * i], Y[3 * i + 1], Y[3 * i + 2]});
+    out[3 * i] = r.x + Pz.t.x; out[3 * i + 1] = r.y + Pz.t.y; out[3 * i + 2] = r.z + Pz.t.z;
   } else if (OP == OP_ACT4) {
-    Pose P = pose_load(X + 7 * i);
-    const float h = Y[4 * i + 3];
-    Vec3 r = qrotate(P.q, {Y[4 * i], Y[4 * i + 1], Y[4 * i + 2]});
-    out[4 * i] = r.x + P.t.x * h; out[4 * i + 1] = r.y + P.t.y * h; out[4 * i + 2] = r.z + P.t.z * h; out[4 * i + 3] = h;
+    const g::P<T> Pz = g::load(X + 7 * i);
+    const T h = Y[4 * i + 3];
+    const g::V<T> r = g::qrotate(Pz.q, g::V<T>{Y[4 * i], Y[4 * i + 1], Y[4 * i + 2]});
+    out[4 * i] = r.x + Pz.t.x * h; out[4 * i + 1] = r.y + Pz.t.y * h; out[4 * i + 2] = r.z + Pz.t.z * h; out[4 * i + 3] = h;
   } else if (OP == OP_MAT) {
-    Pose P = pose_load(X + 7 * i);
-    float R[9];
-    qmatrix(P.q, R);
-    float *T = out + 16 * i;
-    T[0] = R[0]; T[1] = R[1]; T[2] = R[2]; T[3] = P.t.x;
-    T[4] = R[3]; T[5] = R[4]; T[6] = R[5]; T[7] = P.t.y;
-    T[8] = R[6]; T[9] = R[7]; T[10] = R[8]; T[11] = P.t.z;
-    T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
+    const g::P<T> Pz = g::load(X + 7 * i);
+    T R[9];
+    g::qmatrix(Pz.q, R);
+    T *M = out + 16 * i;
+    M[0] = R[0]; M[1] = R[1]; M[2] = R[2]; M[3] = Pz.t.x;
+    M[4] = R[3]; M[5] = R[4]; M[6] = R[5]; M[7] = Pz.t.y;
+    M[8] = R[6]; M[9] = R[7]; M[10] = R[8]; M[11] = Pz.t.z;
+    M[12] = 0; M[13] = 0; M[14] = 0; M[15] = 1;
   }
 }
 
-template <int OP>
-static int launch_se3(const float *X, const float *Y, float *out, int64_t B, void *stream) {
+template <int OP, typename T>
+static int launch_se3(const T *X, const T *Y, T *out, int64_t B, void *stream) {
   if (B < 0 || (B > 0 && (!X || !out))) return BA_ERR_ARG;
   if (B == 0) return BA_OK;
-  k_se3<OP><<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, Y, out, B);
+  k_se3<OP, T><<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, Y, out, B);
   BA_LAUNCH_CHECK();
   return BA_OK;
 }
@@ -94,19 +96,143 @@ __global__ void k_reproject(const float *__restrict__ poses, const float *__rest
   if (valid) valid[e] = Z > kMinDepth ? 1.0f : 0.0f;
 }
 
+
+// transform() with every optional output of projective_ops.py:54-105: the reprojection (with or without the
+// inverse-depth channel of proj(depth=True), :47-50), the validity mask, and the analytic Jacobians Ji, Jj (2x6) and
+// Jz (2x1) of :72-100 — the same edge_terms() the fused BA edge pass uses, materialised for callers that want them.
+__global__ void k_transform_full(const float *__restrict__ poses, const float *__restrict__ patches,
+                                 const float *__restrict__ intr, const int64_t *__restrict__ ii,
+                                 const int64_t *__restrict__ jj, const int64_t *__restrict__ kk, int64_t E,
+                                 int N, int NM, int tonly, int depth, float *__restrict__ coords, float *__restrict__ valid,
+                                 float *__restrict__ Ji, float *__restrict__ Jj, float *__restrict__ Jz) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t i = ii[e], j = jj[e], k = kk[e];
+  const int cs = depth ? 3 : 2;
+  const float nanv = __int_as_float(0x7fc00000);
+  if (i < 0 || i >= N || j < 0 || j >= N || k < 0 || k >= NM) {
+    for (int c = 0; c < cs; ++c) coords[cs * e + c] = nanv;
+    if (valid) valid[e] = 0.0f;
+    if (Ji) for (int c = 0; c < 12; ++c) Ji[12 * e + c] = nanv;
+    if (Jj) for (int c = 0; c < 12; ++c) Jj[12 * e + c] = nanv;
+    if (Jz) { Jz[2 * e] = nanv; Jz[2 * e + 1] = nanv; }
+    return;
+  }
+  Pose G = pose_mul(pose_load(poses + 7 * j), pose_inv(pose_load(poses + 7 * i)));   // :61
+  if (tonly) G.q = {0.0f, 0.0f, 0.0f, 1.0f};                                         // :63-64
+  G.q = qnormalize(G.q);
+  PairConst pc;
+  qmatrix(G.q, pc.R);
+  pc.t = G.t;
+  const float *Ki = intr + 4 * i, *Kj = intr + 4 * j, *p = patches + 3 * k;
+  pc.fxi = Ki[0]; pc.fyi = Ki[1]; pc.cxi = Ki[2]; pc.cyi = Ki[3];
+  pc.fxj = Kj[0]; pc.fyj = Kj[1]; pc.cxj = Kj[2]; pc.cyj = Kj[3];
+  // exact divisions here (this is the materialising path; the fused edge pass uses the SFU forms)
+  const float x0 = (p[0] - pc.cxi) / pc.fxi, y0 = (p[1] - pc.cyi) / pc.fyi, d0 = p[2];
+  const float X = pc.R[0] * x0 + pc.R[1] * y0 + pc.R[2] + pc.t.x * d0;
+  const float Y = pc.R[3] * x0 + pc.R[4] * y0 + pc.R[5] + pc.t.y * d0;
+  const float Z = pc.R[6] * x0 + pc.R[7] * y0 + pc.R[8] + pc.t.z * d0;
+  const float H = d0;
+  const float dc = 1.0f / fmaxf(Z, 1e-2f);                                           // :43
+  coords[cs * e] = pc.fxj * (dc * X) + pc.cxj;
+  coords[cs * e + 1] = pc.fyj * (dc * Y) + pc.cyj;
+  if (depth) coords[cs * e + 2] = dc * H;                                            // :47
+  if (valid) valid[e] = Z > kMinDepth ? 1.0f : 0.0f;                                 // :100 / :103
+  if (Ji || Jj || Jz) {
+    const float dj = fabsf(Z) > kMinDepth ? 1.0f / Z : 0.0f;                         // :80-81
+    const float a = pc.fxj * dj, b = -pc.fxj * X * dj * dj, c = pc.fyj * dj, f = -pc.fyj * Y * dj * dj;
+    float J0[6] = {a * H, 0.0f, b * H, b * Y, a * Z - b * X, -a * Y};                // Jp Ja, :83-95
+    float J1[6] = {0.0f, c * H, f * H, -c * Z + f * Y, -f * X, c * X};
+    if (Jj) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) { Jj[12 * e + q] = J0[q]; Jj[12 * e + 6 + q] = J1[q]; }
+    }
+    if (Ji) {                                                                        // Ji = -Ad(Gij)^T Jj, :96
+      float o0[6], o1[6];
+      adjT_apply(pc.R, pc.t, J0, o0);
+      adjT_apply(pc.R, pc.t, J1, o1);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) { Ji[12 * e + q] = -o0[q]; Ji[12 * e + 6 + q] = -o1[q]; }
+    }
+    if (Jz) {                                                                        // Jp * Gij.matrix()[:, 3], :98
+      Jz[2 * e] = a * pc.t.x + b * pc.t.z;
+      Jz[2 * e + 1] = c * pc.t.y + f * pc.t.z;
+    }
+  }
+}
+
+// point_cloud (projective_ops.py:107-109): T_ix^-1 * iproj(patch), one thread per patch
+__global__ void k_point_cloud(const float *__restrict__ poses, const float *__restrict__ patches,
+                              const float *__restrict__ intr, const int64_t *__restrict__ ix, int64_t n, int N,
+                              float *__restrict__ out) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int64_t f = ix[k];
+  if (f < 0 || f >= N) { for (int c = 0; c < 4; ++c) out[4 * k + c] = __int_as_float(0x7fc00000); return; }
+  const Pose Ti = pose_inv(pose_load(poses + 7 * f));
+  const float *K = intr + 4 * f, *p = patches + 3 * k;
+  const float x0 = (p[0] - K[2]) / K[0], y0 = (p[1] - K[3]) / K[1], d = p[2];
+  Pose Tl = Ti;
+  Tl.q = qnormalize(Ti.q);                                                  // act4 re-loads (normalises) its operand
+  const Vec3 r = qrotate(Tl.q, {x0, y0, 1.0f});
+  out[4 * k] = r.x + Tl.t.x * d; out[4 * k + 1] = r.y + Tl.t.y * d; out[4 * k + 2] = r.z + Tl.t.z * d; out[4 * k + 3] = d;
+}
+
+// back_proj (projective_ops.py:129-152): pixel + depth -> homogeneous camera (or world, with c2w) point
+__global__ void k_back_proj(const float *__restrict__ xy, const float *__restrict__ depth, const float *__restrict__ intr,
+                            const float *__restrict__ c2w, int B, int64_t n, float *__restrict__ P) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * n) return;
+  const int b = (int)(idx / n);
+  const float *K = intr + 4 * b;
+  const float D = depth[idx];
+  const float X = (xy[2 * idx] - K[2]) / K[0], Y = (xy[2 * idx + 1] - K[3]) / K[1];
+  float v[4] = {X * D, Y * D, D, 1.0f};
+  if (c2w) {
+    const float *T = c2w + 16 * b;
+    float o[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) o[r] = T[4 * r] * v[0] + T[4 * r + 1] * v[1] + T[4 * r + 2] * v[2] + T[4 * r + 3] * v[3];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) v[r] = o[r];
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) P[4 * idx + r] = v[r];
+}
+
+// proj_to_frames (projective_ops.py:154-176): world points into S cameras, plain 1/Z like the reference
+__global__ void k_proj_to_frames(const float *__restrict__ P, const float *__restrict__ intr, const float *__restrict__ w2c,
+                                 int B, int S, int64_t n, float *__restrict__ xy) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * S * n) return;
+  const int64_t bs = idx / n, k = idx - bs * n;
+  const int b = (int)(bs / S);
+  const float *T = w2c + 16 * bs, *K = intr + 4 * bs, *p = P + 4 * ((int64_t)b * n + k);
+  const float Xc = T[0] * p[0] + T[1] * p[1] + T[2] * p[2] + T[3] * p[3];
+  const float Yc = T[4] * p[0] + T[5] * p[1] + T[6] * p[2] + T[7] * p[3];
+  const float Dc = T[8] * p[0] + T[9] * p[1] + T[10] * p[2] + T[11] * p[3];
+  const float dc = 1.0f / Dc;
+  xy[2 * idx] = K[0] * (Xc * dc) + K[2];
+  xy[2 * idx + 1] = K[1] * (Yc * dc) + K[3];
+}
+
 }  // namespace ba
 
 using namespace ba;
 
-extern "C" int se3_expm(const float *a, float *X, int64_t B, void *s) { return launch_se3<OP_EXP>(a, nullptr, X, B, s); }
-extern "C" int se3_logm(const float *X, float *a, int64_t B, void *s) { return launch_se3<OP_LOG>(X, nullptr, a, B, s); }
-extern "C" int se3_inv(const float *X, float *Y, int64_t B, void *s) { return launch_se3<OP_INV>(X, nullptr, Y, B, s); }
-extern "C" int se3_mul(const float *X, const float *Y, float *Z, int64_t B, void *s) { return (B > 0 && !Y) ? BA_ERR_ARG : launch_se3<OP_MUL>(X, Y, Z, B, s); }
-extern "C" int se3_adj(const float *X, const float *a, float *b, int64_t B, void *s) { return (B > 0 && !a) ? BA_ERR_ARG : launch_se3<OP_ADJ>(X, a, b, B, s); }
-extern "C" int se3_adjT(const float *X, const float *a, float *b, int64_t B, void *s) { return (B > 0 && !a) ? BA_ERR_ARG : launch_se3<OP_ADJT>(X, a, b, B, s); }
-extern "C" int se3_act(const float *X, const float *p, float *q, int64_t B, void *s) { return (B > 0 && !p) ? BA_ERR_ARG : launch_se3<OP_ACT>(X, p, q, B, s); }
-extern "C" int se3_act4(const float *X, const float *p, float *q, int64_t B, void *s) { return (B > 0 && !p) ? BA_ERR_ARG : launch_se3<OP_ACT4>(X, p, q, B, s); }
-extern "C" int se3_as_matrix(const float *X, float *T, int64_t B, void *s) { return launch_se3<OP_MAT>(X, nullptr, T, B, s); }
+#define SE3_ENTRY(PFX, T)                                                                                                   \
+  extern "C" int PFX##_expm(const T *a, T *X, int64_t B, void *s) { return launch_se3<OP_EXP, T>(a, nullptr, X, B, s); }      \
+  extern "C" int PFX##_logm(const T *X, T *a, int64_t B, void *s) { return launch_se3<OP_LOG, T>(X, nullptr, a, B, s); }      \
+  extern "C" int PFX##_inv(const T *X, T *Y, int64_t B, void *s) { return launch_se3<OP_INV, T>(X, nullptr, Y, B, s); }       \
+  extern "C" int PFX##_mul(const T *X, const T *Y, T *Z, int64_t B, void *s) { return (B > 0 && !Y) ? BA_ERR_ARG : launch_se3<OP_MUL, T>(X, Y, Z, B, s); }   \
+  extern "C" int PFX##_adj(const T *X, const T *a, T *b, int64_t B, void *s) { return (B > 0 && !a) ? BA_ERR_ARG : launch_se3<OP_ADJ, T>(X, a, b, B, s); }   \
+  extern "C" int PFX##_adjT(const T *X, const T *a, T *b, int64_t B, void *s) { return (B > 0 && !a) ? BA_ERR_ARG : launch_se3<OP_ADJT, T>(X, a, b, B, s); } \
+  extern "C" int PFX##_act(const T *X, const T *p, T *q, int64_t B, void *s) { return (B > 0 && !p) ? BA_ERR_ARG : launch_se3<OP_ACT, T>(X, p, q, B, s); }   \
+  extern "C" int PFX##_act4(const T *X, const T *p, T *q, int64_t B, void *s) { return (B > 0 && !p) ? BA_ERR_ARG : launch_se3<OP_ACT4, T>(X, p, q, B, s); } \
+  extern "C" int PFX##_as_matrix(const T *X, T *M, int64_t B, void *s) { return launch_se3<OP_MAT, T>(X, nullptr, M, B, s); }
+SE3_ENTRY(se3, float)
+SE3_ENTRY(se3d, double)
+#undef SE3_ENTRY
 
 extern "C" int ba_reproject(const float *poses, const float *patches, const float *intrinsics, const int64_t *ii,
                             const int64_t *jj, const int64_t *kk, int64_t E, int32_t N, int32_t NM, int32_t tonly,
@@ -116,6 +242,48 @@ extern "C" int ba_reproject(const float *poses, const float *patches, const floa
   if (!poses || !patches || !intrinsics || !ii || !jj || !kk || !coords) return BA_ERR_ARG;
   k_reproject<<<(unsigned)((E + 255) / 256), 256, 0, (cudaStream_t)stream>>>(poses, patches, intrinsics, ii, jj, kk, E,
                                                                             N, NM, tonly, coords, valid);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+extern "C" int ba_transform(const float *poses, const float *patches, const float *intrinsics, const int64_t *ii,
+                            const int64_t *jj, const int64_t *kk, int64_t E, int32_t N, int32_t NM, int32_t tonly,
+                            int32_t depth, float *coords, float *valid, float *Ji, float *Jj, float *Jz, void *stream) {
+  if (E < 0 || N <= 0 || NM <= 0) return BA_ERR_ARG;
+  if (E == 0) return BA_OK;
+  if (!poses || !patches || !intrinsics || !ii || !jj || !kk || !coords) return BA_ERR_ARG;
+  k_transform_full<<<(unsigned)((E + 255) / 256), 256, 0, (cudaStream_t)stream>>>(poses, patches, intrinsics, ii, jj, kk, E, N, NM,
+                                                                                  tonly, depth, coords, valid, Ji, Jj, Jz);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+extern "C" int ba_point_cloud(const float *poses, const float *patches, const float *intrinsics, const int64_t *ix,
+                              int64_t n, int32_t N, float *out, void *stream) {
+  if (n < 0 || N <= 0) return BA_ERR_ARG;
+  if (n == 0) return BA_OK;
+  if (!poses || !patches || !intrinsics || !ix || !out) return BA_ERR_ARG;
+  k_point_cloud<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(poses, patches, intrinsics, ix, n, N, out);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+extern "C" int ba_back_proj(const float *xy, const float *depth, const float *intrinsics, const float *c2w, int32_t B,
+                            int64_t n, float *P, void *stream) {
+  if (B < 0 || n < 0) return BA_ERR_ARG;
+  if ((int64_t)B * n == 0) return BA_OK;
+  if (!xy || !depth || !intrinsics || !P) return BA_ERR_ARG;
+  k_back_proj<<<(unsigned)(((int64_t)B * n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(xy, depth, intrinsics, c2w, B, n, P);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+extern "C" int ba_proj_to_frames(const float *P, const float *intrinsics, const float *w2c, int32_t B, int32_t S, int64_t n,
+                                 float *xy, void *stream) {
+  if (B < 0 || S < 0 || n < 0) return BA_ERR_ARG;
+  if ((int64_t)B * S * n == 0) return BA_OK;
+  if (!P || !intrinsics || !w2c || !xy) return BA_ERR_ARG;
+  k_proj_to_frames<<<(unsigned)(((int64_t)B * S * n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, intrinsics, w2c, B, S, n, xy);
   BA_LAUNCH_CHECK();
   return BA_OK;
 }
@@ -152,8 +320,12 @@ void host_pipe_destroy(void *p_) {
 }
 }  // namespace
 
-extern "C" int ba_step_host_async(BaPlan *pl, const BaProblem *ph, void *stream_) {
-  if (!pl || !ph || !ph->poses || !ph->patches || !ph->intrinsics || !ph->targets || !ph->weights ||
+// Upload half: the host arrays of `ph` go to the next staging slot on the plan's upload stream, `stream` is made to wait
+// for them (and for the previous user of the slot), and `pd` receives the device-side problem (outputs pointing into
+// the slot). Download half (ba_unstage_host_async): once `stream` has computed, the two results return to the host
+// arrays of `ph` on the download stream.
+extern "C" int ba_stage_host_async(BaPlan *pl, const BaProblem *ph, BaProblem *pd_out, void *stream_) {
+  if (!pl || !ph || !pd_out || !ph->poses || !ph->patches || !ph->intrinsics || !ph->targets || !ph->weights ||
       !ph->poses_out || !ph->patches_out)
     return BA_ERR_ARG;
   if (ph->targets_stride != 0 && ph->targets_stride != 2) return BA_ERR_ARG;
@@ -203,15 +375,32 @@ extern "C" int ba_step_host_async(BaPlan *pl, const BaProblem *ph, void *stream_
   if (hp->seq >= 2) BA_CUDA(cudaStreamWaitEvent(s, hp->out_done[slot], 0));          // results of call seq-2 downloaded
   pd.poses_out = (float *)(d + o_pout);
   pd.patches_out = (float *)(d + o_qout);
-  int rc = ba_step(pl, &pd, stream_);
-  if (rc) return rc;
+  *pd_out = pd;
+  return BA_OK;
+}
+
+extern "C" int ba_unstage_host_async(BaPlan *pl, const BaProblem *ph, const BaProblem *pd, void *stream_) {
+  if (!pl || !ph || !pd || !pl->host_pipe || !ph->poses_out || !ph->patches_out) return BA_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream_;
+  HostPipe *hp = static_cast<HostPipe *>(pl->host_pipe);
+  const size_t N = pl->v.N, NM = pl->v.NM, f = sizeof(float);
+  const int slot = (int)(hp->seq & 1);
   BA_CUDA(cudaEventRecord(hp->computed[slot], s));
   BA_CUDA(cudaStreamWaitEvent(hp->d2h, hp->computed[slot], 0));
-  BA_CUDA(cudaMemcpyAsync(ph->poses_out, pd.poses_out, 7 * N * f, cudaMemcpyDeviceToHost, hp->d2h));
-  BA_CUDA(cudaMemcpyAsync(ph->patches_out, pd.patches_out, 3 * NM * f, cudaMemcpyDeviceToHost, hp->d2h));
+  BA_CUDA(cudaMemcpyAsync(ph->poses_out, pd->poses_out, 7 * N * f, cudaMemcpyDeviceToHost, hp->d2h));
+  BA_CUDA(cudaMemcpyAsync(ph->patches_out, pd->patches_out, 3 * NM * f, cudaMemcpyDeviceToHost, hp->d2h));
   BA_CUDA(cudaEventRecord(hp->out_done[slot], hp->d2h));
   hp->seq++;
   return BA_OK;
+}
+
+extern "C" int ba_step_host_async(BaPlan *pl, const BaProblem *ph, void *stream_) {
+  BaProblem pd;
+  int rc = ba_stage_host_async(pl, ph, &pd, stream_);
+  if (rc) return rc;
+  rc = ba_step(pl, &pd, stream_);
+  if (rc) return rc;
+  return ba_unstage_host_async(pl, ph, &pd, stream_);
 }
 
 // Orders `stream` after the download of every call submitted so far (so an event recorded on it next sees the

@@ -104,6 +104,7 @@ struct BaOptions {
   int spin_cap;        // BA_OPT_SPIN_CAP
   int trace;           // BA_OPT_SOLVER_TRACE
   int schur;           // BA_OPT_SCHUR: 0 tcgen05 (tensor-core) Schur kernel where it applies, 1 SIMT kernel
+  int schur_acc;       // BA_OPT_SCHUR_ACC: chunks of 32 tracks accumulated in TMEM (fp32) before the fp64 read-back
 };
 
 struct BaPlan {
@@ -171,6 +172,11 @@ int solve_diag_prepare_device();
 int solve_mma_prepare_device(int dev, cudaStream_t s);
 int kernels_prepare_device();
 int schur_tc_prepare_device();
+constexpr int kSchurTcMaxFree = 21;     // free pose slots of a group the tensor-core Schur kernel covers (6 * 21 + 1 <= 128 rows)
+int launch_schur_tc(const PlanView &pv, const CallView &cv, int n_units, const int *ut0, const int *ugrp, const int *order,
+                    int *flags, int epoch, int acc_chunks, int min_tracks, cudaStream_t s);
+constexpr int kSchurTcMinTracks = 96;   // shorter units stay on the SIMT kernel (faster there, and the 8-keyframe class of
+                                        // ill-conditioned small windows keeps plain fp32 products)
 }  // namespace ba
 
 namespace ba {

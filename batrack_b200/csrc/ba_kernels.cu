@@ -811,7 +811,7 @@ constexpr int kSchurPad = 2;      // floats of padding per staged row: 8-byte lo
 // the units that feed them are complete (SolveFeed, ba_solve_mma.cu).
 __global__ void __launch_bounds__(kSchurThreads, 2) k_schur(PlanView pv, CallView cv, int tile_tracks, const int *__restrict__ ut0,
                                                             const int *__restrict__ ugrp, const int *__restrict__ order,
-                                                            int *__restrict__ flags, int epoch) {
+                                                            int *__restrict__ flags, int epoch, int tc_on) {   // tc_on: min tracks of a tensor-core unit, 0 = off
   constexpr int NT = kSchurThreads;
   extern __shared__ __align__(16) float smem[];
   const int tau = threadIdx.x;
@@ -822,6 +822,11 @@ __global__ void __launch_bounds__(kSchurThreads, 2) k_schur(PlanView pv, CallVie
   const int W = pv.g_W[g];
   const int rowlen = 6 * W;
   const int *slot_pose = pv.slot_pose + 2 * pv.g_pat[g];
+  if (tc_on) {                                     // units whose free slots fit 128 operand rows belong to k_schur_tc
+    int nf = 0;
+    for (int s = 0; s < W; ++s) nf += pose_free(slot_pose[s], cv) ? 1 : 0;
+    if (nf <= kSchurTcMaxFree && t1 - t0 >= tc_on) return;
+  }
   const float *Erows = cv.Est + pv.g_eoff[g];
   const int Ts = (pv.g_t0[g + 1] - gt0 + 3) & ~3;
   const int ts = tile_tracks + kSchurPad;
@@ -1183,6 +1188,9 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve_dense(CallView cv, int 
 //     consecutive threads (consecutive tracks of a group) read consecutive floats; the pose of a slot and its dX
 //     are uniform across the threads of a group.
 // =================================================================================================
+// torch.clamp propagates NaN (ba.py:333); fminf / fmaxf would return the bound instead
+__device__ __forceinline__ float clamp_disp(float v) { return v != v ? v : fminf(fmaxf(v, 1e-3f), 10.0f); }
+
 __device__ __forceinline__ void pose_retr_one(const CallView &cv, int i) {
   float a[6] = {0, 0, 0, 0, 0, 0};
   if (pose_free(i, cv)) {
@@ -1216,7 +1224,7 @@ __global__ void __launch_bounds__(256) k_backsub(PlanView pv, CallView cv, int u
     if (k >= pv.NM || pv.patch_track[k] >= 0) return;
     cv.patches_out[3 * (size_t)k] = cv.patches[3 * (size_t)k];
     cv.patches_out[3 * (size_t)k + 1] = cv.patches[3 * (size_t)k + 1];
-    cv.patches_out[3 * (size_t)k + 2] = fminf(fmaxf(cv.patches[3 * (size_t)k + 2], 1e-3f), 10.0f);   // clamp hits every patch, ba.py:333
+    cv.patches_out[3 * (size_t)k + 2] = clamp_disp(cv.patches[3 * (size_t)k + 2]);   // clamp hits every patch, ba.py:333
     return;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1256,7 +1264,7 @@ __global__ void __launch_bounds__(256) k_backsub(PlanView pv, CallView cv, int u
     const size_t k = (size_t)pv.kx[t];
     cv.patches_out[3 * k] = cv.patches[3 * k];
     cv.patches_out[3 * k + 1] = cv.patches[3 * k + 1];
-    cv.patches_out[3 * k + 2] = fminf(fmaxf(cv.patches[3 * k + 2] + dz, 1e-3f), 10.0f);
+    cv.patches_out[3 * k + 2] = clamp_disp(cv.patches[3 * k + 2] + dz);
   }
 }
 
@@ -1372,6 +1380,10 @@ static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int str
     while (tile > 4 && (size_t)kSchurStages * (rowmax * (tile + kSchurPad) + 2 * tile) * sizeof(float) > 100 * 1024) tile -= 4;
     const size_t smem = (size_t)kSchurStages * (rowmax * (tile + kSchurPad) + 2 * tile) * sizeof(float);
     if (smem > 200 * 1024) return BA_ERR_ARG;
+    // tensor-core kernel (tcgen05, 3xTF32) for every unit whose free pose slots fit 128 operand rows; the SIMT kernel
+    // takes the rest (and everything with BA_OPT_SCHUR = 1)
+    const bool tc = pl->opt.schur == 0;
+    const bool simt = true;                // it also takes the units shorter than kSchurTcMinTracks (exits at once elsewhere)
     if (streaming) {
       int *flags = reinterpret_cast<int *>(cv.y + cv.M);
       const SolveFeed feed = make_feed(pl, flags, pv.top_need, pv.bot_need, 1, pv.n_ounits, pb->fixedp, 1, pl->status + 2);
@@ -1380,10 +1392,14 @@ static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int str
       if (rc) return rc;
       BA_CUDA(cudaEventRecord(pl->ev_solved, pl->solve_stream));
       const size_t stream_smem = (size_t)pl->opt.stream_smem_kb * 1024;   // BA_OPT_STREAM_SMEM_KB: throttle occupancy (tests force the give-up path with it)
-      k_schur<<<pv.n_ounits, kSchurThreads, std::max(smem, stream_smem), s>>>(pv, cv, tile, pv.o_t0, pv.o_grp, pv.o_order, flags, 1);
-      BA_LAUNCH_CHECK();
+      if (tc) { rc = launch_schur_tc(pv, cv, pv.n_ounits, pv.o_t0, pv.o_grp, pv.o_order, flags, 1, pl->opt.schur_acc, kSchurTcMinTracks, s); if (rc) return rc; }
+      if (simt) {
+        k_schur<<<pv.n_ounits, kSchurThreads, std::max(smem, stream_smem), s>>>(pv, cv, tile, pv.o_t0, pv.o_grp, pv.o_order, flags, 1, tc ? kSchurTcMinTracks : 0);
+        BA_LAUNCH_CHECK();
+      }
     } else {
-      k_schur<<<pv.n_units, kSchurThreads, smem, s>>>(pv, cv, tile, pv.u_t0, pv.u_grp, nullptr, nullptr, 0); BA_LAUNCH_CHECK();
+      if (tc) { rc = launch_schur_tc(pv, cv, pv.n_units, pv.u_t0, pv.u_grp, nullptr, nullptr, 0, pl->opt.schur_acc, kSchurTcMinTracks, s); if (rc) return rc; }
+      if (simt) { k_schur<<<pv.n_units, kSchurThreads, smem, s>>>(pv, cv, tile, pv.u_t0, pv.u_grp, nullptr, nullptr, 0, tc ? kSchurTcMinTracks : 0); BA_LAUNCH_CHECK(); }
     }
   }
   BA_MARK(pl, BA_STAGE_SOLVE, s);      // closes SCHUR; a sharded caller's all-reduce lands in SOLVE's interval

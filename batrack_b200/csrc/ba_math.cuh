@@ -203,11 +203,13 @@ BA_HD void edge_terms(const PairConst &c, float ifxi, float ifyi, float px, floa
   bool ok = Z > kMinDepth;
   ok = ok && (r0 * r0 + r1 * r1 < 250.0f * 250.0f);      // ||r|| < 250
   ok = ok && (o.u > bounds[0]) && (o.v > bounds[1]) && (o.u < bounds[2]) && (o.v < bounds[3]);
+  // the mask MULTIPLIES like the reference's (ba.py:241-242, :250): a NaN / inf target or weight of a rejected edge still
+  // poisons the sums exactly as it does there (0 * NaN = NaN), which is what reaches the NaN retry of ba.py:324-325
   o.valid = ok ? 1.0f : 0.0f;
-  o.w0 = ok ? wx * robust_weight(r0, loss) : 0.0f;
-  o.w1 = ok ? wy * robust_weight(r1, loss) : 0.0f;
-  o.r0 = ok ? r0 : 0.0f;
-  o.r1 = ok ? r1 : 0.0f;
+  o.w0 = o.valid * (wx * robust_weight(r0, loss));
+  o.w1 = o.valid * (wy * robust_weight(r1, loss));
+  o.r0 = o.valid * r0;
+  o.r1 = o.valid * r1;
 }
 
 // index of (a,b), a >= b, in a packed lower-triangular 6x6 (21 entries)

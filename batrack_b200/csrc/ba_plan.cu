@@ -365,6 +365,7 @@ static void options_from_env(BaOptions *o) {
   o->spin_cap = std::max(0, env_int("BA_SPIN_CAP", 0));
   o->trace = env_int("BA_SOLVER_TRACE", 0) ? 1 : 0;
   o->schur = env_int("BA_SCHUR", 0) ? 1 : 0;
+  o->schur_acc = std::min(8, std::max(1, env_int("BA_SCHUR_ACC", 2)));
 }
 template <typename T> static cudaError_t own(BaPlan *pl, T **p, size_t n) {
   void *q = nullptr;
@@ -687,6 +688,7 @@ extern "C" int ba_plan_set_option(BaPlan *pl, int32_t key, int32_t value) {
       pl->opt.trace = value ? 1 : 0;
       break;
     case BA_OPT_SCHUR: if (value < 0 || value > 1) return BA_ERR_ARG; pl->opt.schur = value; break;
+    case BA_OPT_SCHUR_ACC: if (value < 1 || value > 8) return BA_ERR_ARG; pl->opt.schur_acc = value; break;
     default: return BA_ERR_ARG;
   }
   return BA_OK;
@@ -703,6 +705,7 @@ extern "C" int ba_plan_get_option(const BaPlan *pl, int32_t key, int32_t *value)
     case BA_OPT_SPIN_CAP: *value = pl->opt.spin_cap; break;
     case BA_OPT_SOLVER_TRACE: *value = pl->opt.trace; break;
     case BA_OPT_SCHUR: *value = pl->opt.schur; break;
+    case BA_OPT_SCHUR_ACC: *value = pl->opt.schur_acc; break;
     default: return BA_ERR_ARG;
   }
   return BA_OK;

@@ -33,8 +33,22 @@ namespace ba {
 
 namespace {
 
-constexpr int kNW = 8;                        // tile warps
-constexpr int kThreadsDg = 32 * (kNW + 1);    // + the factor warp
+constexpr int kNW = 9;                        // tile warps (hardware warps 1-3, 5-7, 9-11: three per scheduler 1-3)
+constexpr int kNP = 2;                        // panel warps (hardware warps 4, 8: scheduler 0, next to the factor warp). Twelve
+                                              // warps in all: a thirteenth would cap the kernel at 128 registers per thread
+                                              // (warps are allocated in fours), and the tile warps need ~170
+constexpr int kPanelTiles = 8;                // panel tiles per panel warp (8 + 7)
+constexpr int kThreadsDg = 32 * (kNW + kNP + 1);   // all 12 warps; hardware warp 0 is the factor warp
+constexpr int kHwThreadsDg = kThreadsDg;
+// named barriers (id 0 is __syncthreads); [p] = parity of the tile column
+constexpr int kBarP = 1;                      // 1, 2: panel tiles of column J stored      (panel warps arrive, tile warps wait)
+constexpr int kBarA = 3;                      // 3, 4: next column's A tiles shipped        (tile warps arrive, panel + factor warps wait)
+constexpr int kBarW = 5;                      // 5, 6: W_J / zJ (or the failure flag) ready (factor warp arrives, panel warps wait)
+constexpr int kBarD = 7;                      // diagonal tile published                    (warp of diagonal 0 -> factor warp)
+constexpr int kBarX = 8;                      // x_J of the back substitution
+constexpr int kBarZ = 9;                      // twist hand-over: z of the middle complete (tile warps)
+constexpr int kBarN = 10;                     // 10, 11: tile (J+1,J+1) without column J's update shipped (warp of diagonal 0 -> factor warp)
+constexpr int kCntP = 32 * (kNW + kNP), kCntA = 32 * (kNW + kNP + 1), kCntW = 32 * (kNP + 1);
 constexpr int kBackStages = 4;                // tile rows of L in flight during the back substitution
 constexpr int kPs = 12;                       // row stride (doubles) of the shared diagonal tile
 
@@ -73,15 +87,21 @@ __device__ __forceinline__ void cluster_sync() {
 // last Jm1 tile columns, working on the index-reversed matrix (same code, reversed coordinates); CTA 1 then hands
 // CTA 0 what its eliminations contributed to the 16 middle tile columns, CTA 0 finishes the middle, solves it, and
 // both back-substitute their side in parallel. Exchange through global scratch XD + cluster barriers.
-__global__ void __launch_bounds__(kThreadsDg, 1) k_solve_band_diag(CallView cv, int allow_retry, double *__restrict__ L_all,
+__global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv, int allow_retry, double *__restrict__ L_all,
                                                                    double *__restrict__ XD, int *__restrict__ gfl, int twist,
                                                                    long long *__restrict__ trace, SolveFeed feed) {
   extern __shared__ __align__(16) double dsm[];
   // mode 2: stand-by launch behind a streaming one — runs only if that one gave up (its producer was not running
   // concurrently: kernels serialised by a profiler / sanitizer), as a plain solve of the by now complete system
   if (feed.mode == 2 && *reinterpret_cast<const volatile int *>(feed.redo) == 0) return;
-  const int tau = threadIdx.x, lane = tau & 31, warp = tau >> 5;
-  const bool is_factor = warp == kNW, is_tile = warp < kNW;
+  // The 8x8 factorisation is a dependent FP64 chain: behind two DMMA warps on its scheduler it runs 3.3x slower than
+  // alone (tools/microbench_factor.cu: 674 -> 2216 cycles). Scheduler 0 therefore holds the factor warp and the two
+  // panel warps, which only work while the factor warp waits for the next diagonal tile; the nine tile warps (the
+  // DMMA-bound trailing update) sit three per scheduler on schedulers 1-3.
+  const int lane = threadIdx.x & 31, hw = threadIdx.x >> 5;
+  const int warp = hw == 0 ? kNW + kNP : ((hw & 3) == 0 ? kNW + (hw >> 2) - 1 : hw - 1 - (hw >> 2));   // logical warp
+  const int tau = 32 * warp + lane;                                 // logical thread id: tile warps first
+  const bool is_factor = warp == kNW + kNP, is_tile = warp < kNW, is_panel = !is_factor && !is_tile;
   const int g = lane >> 2, q = lane & 3;
   const int M = cv.M, bw = cv.bw, ld = cv.ld, off = cv.off;
   const int NT8 = (M + 7) >> 3, Mp = NT8 * 8;
@@ -96,13 +116,18 @@ __global__ void __launch_bounds__(kThreadsDg, 1) k_solve_band_diag(CallView cv, 
   auto Lg = [&](int rl, int cl) { return (size_t)rl * 128 + (cl - 8 * (rl >> 3) + 120); };
   double *z = dsm;                         // [Mp]   right-hand side -> forward solution -> solution
   double *dd = z + Mp;                     // [Mp]   damping ep + lm * S_rr, added when a diagonal tile is factored
-  double *Psm = dd + Mp;                   // [16][64] panel tiles L_{J+i,J}, i = 1..15, operand layout
-  double *Dsm = Psm + 16 * 64;             // [8][kPs] diagonal tile handed to the factor warp
-  double *Wsm = Dsm + 8 * kPs;             // [64]     -W = -L_JJ^-1, operand layout
-  double *zJ = Wsm + 64;                   // [8]
-  double *Lst = zJ + 8;                    // [kBackStages][8][128] back-substitution stages
+  double *Psm = dd + Mp;                   // [2][16][64] panel tiles L_{J+i,J}, i = 1..15, operand layout, by column parity
+  double *Asm = Psm + 2 * 16 * 64;         // [2][16][64] -A_{J+i,J} (what the panel warps turn into L), operand layout
+  double *Dsm = Asm + 2 * 16 * 64;         // [8][kPs] diagonal tile handed to the factor warp
+  double *Wsm = Dsm + 8 * kPs;             // [2][64]  -W = -L_JJ^-1, operand layout
+  double *zJ = Wsm + 2 * 64;               // [2][8]
+  double *Dnsm = zJ + 2 * 8;               // [2][64]  -D_{J+1} without column J's update, C layout [g][c] (diagonal 0 -> factor warp)
+  double *Fsm = Dnsm + 2 * 64;             // [64]     factor warp: L_{J+1,J} in operand layout
+  double *Hsm = Fsm + 64;                  // [64]     twist hand-over: -D_{c1} back from the factor warp, C layout
+  double *Lst = Hsm + 64;                  // [kBackStages][8][128] back-substitution stages
   double *xsol = dd;                       // solution of the back substitution (dd is dead then)
   __shared__ int s_fail, s_nan, s_abort;
+  __shared__ volatile int s_colfail[2];      // the failure flag of the column of each parity (the factor warp runs one column ahead)
   __shared__ __align__(8) unsigned long long s_mbar[kBackStages];
   constexpr int kIssueThread = 160;        // lane 0 of tile warp 5: issues the stage copies
   int bs_it = 0;
@@ -177,7 +202,7 @@ __global__ void __launch_bounds__(kThreadsDg, 1) k_solve_band_diag(CallView cv, 
     if (feed.flags) {                                              // the first window (16 tile rows) must be complete
       if (tau == 0) { s_cursor = 0; s_giveup = 0; }
       __syncthreads();
-      const int need0 = need_of(min(15, NTloc - 1));
+      const int need0 = need_of(min(17, NTloc - 1));
       if (is_factor) {
         wcur = 0;
         int spins = 0;
@@ -188,14 +213,22 @@ __global__ void __launch_bounds__(kThreadsDg, 1) k_solve_band_diag(CallView cv, 
       __syncthreads();
       __threadfence();
     }
-    const int rows_now = feed.flags ? min(Mp, 128) : Mp;
+    const int rows_now = feed.flags ? min(Mp, 144) : Mp;             // tile rows 0..17; later rows are fetched as they enter
     for (int rl = tau; rl < rows_now; rl += kThreadsDg) load_row(rl);
-    if (tau == 0) { s_fail = (feed.flags && s_giveup) ? 1 : 0; s_nan = 0; s_abort = 0; }
+    if (tau == 0) { s_fail = (feed.flags && s_giveup) ? 1 : 0; s_nan = 0; s_abort = 0; s_colfail[0] = s_colfail[1] = 0; }
     int *gf = gfl + 4 * attempt;                                   // [0] side 0 failed, [1] side 1 failed, [2] NaN
     __syncthreads();
     const int nsegs = twist ? 2 : 1;
+    // a hand-over segment (segment 0 of a twisted solve) keeps the pipeline one column past its end: the exchange
+    // needs the tiles the factor warp and the warp of diagonal 0 hold for column c1
+    const int oc0 = ((2 * q) & 3) * 2 + ((2 * q) >> 2), oc1 = ((2 * q + 1) & 3) * 2 + ((2 * q + 1) >> 2);
     if (is_factor) {
-      // =================== factor warp: [A] for column J while the tile warps still update column J-1 ==========
+      // =================== factor warp: the whole critical chain of the factorisation =============================
+      //   [A]  8x8 Cholesky of the diagonal tile, W_J = L_JJ^-1, zJ                       (every lane redundantly)
+      //   [L]  L_{J+1,J} = A_{J+1,J} W_J^T  (2 DMMAs; -A_{J+1,J} was shipped by the warp of diagonal 1 a column ago)
+      //   [D]  D_{J+1} = D_{J+1} - L L^T + damping  (2 DMMAs; D_{J+1} with the updates of columns <= J-1 was shipped by
+      //        the warp of diagonal 0 a column ago), z_{J+1} -= L zJ
+      // so the next [A] never waits for the tile warps' DMMA queues: they only have to stay less than a column behind.
       for (int seg = 0; seg < nsegs; ++seg) {
         if (seg == 1) {                                            // twist hand-over (see the tile-warp branch)
           __syncthreads();
@@ -203,8 +236,11 @@ __global__ void __launch_bounds__(kThreadsDg, 1) k_solve_band_diag(CallView cv, 
           __syncthreads();
         }
         const int jb = seg ? c1 : 0, je = seg ? ((side == 0 && !s_abort) ? NTloc : c1) : c1;
+        const bool handover = twist && seg == 0;
         bool stop = false;
+        if (jb < je) bar_sync(kBarD, 64);                          // tile (jb,jb) (+ damping) is in Dsm
         for (int J = jb; J < je; ++J) {
+          const int p = J & 1;
           BA_TR(8);
           if (feed.flags && wcur < feed.n_units) {
             if (probe_on) {
@@ -212,7 +248,7 @@ __global__ void __launch_bounds__(kThreadsDg, 1) k_solve_band_diag(CallView cv, 
               const int adv = mk == 0xffffffffu ? 32 : __ffs(~mk) - 1;
               if (adv) { wcur += adv; __threadfence(); if (lane == 0) s_cursor = wcur; }
             }
-            const int nd = J + 16 < NTloc ? need_of(J + 16) : 0;
+            const int nd = J + 18 < NTloc ? need_of(J + 18) : 0;
             int spins = 0;
             while (wcur < nd && !s_giveup && ++spins < (spin_cap >> 4) + 8) poll();
             if (wcur < nd && lane == 0) s_giveup = 1;
@@ -222,13 +258,13 @@ __global__ void __launch_bounds__(kThreadsDg, 1) k_solve_band_diag(CallView cv, 
           }
           if (feed.flags && (s_giveup || s_fail)) {                // the producer is not there: leave like a failed pivot
             __syncwarp();
-            if (lane == 0) s_fail = 1;
+            if (lane == 0) { s_fail = 1; s_colfail[p] = 1; }
             __syncwarp();
-            bar_arrive(3, 32 * (kNW + 1));
+            bar_arrive(kBarW + p, kCntW);
+            bar_sync(kBarA + p, kCntA);                            // keep the count of this column's barrier whole
             stop = true;
             break;
           }
-          bar_sync(2, 64);                                         // tile (J,J) (+ damping) is in Dsm, z_J is final
           double a[36];
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -265,25 +301,273 @@ __global__ void __launch_bounds__(kThreadsDg, 1) k_solve_band_diag(CallView cv, 
           if (ok) {
             if (lane < 8) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) Wsm[op_idx(i, lane)] = -wv[i];
+              for (int i = 0; i < 8; ++i) Wsm[64 * p + op_idx(i, lane)] = -wv[i];
             } else if (lane == 8) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { z[8 * J + i] = wv[i]; zJ[i] = wv[i]; }
+              for (int i = 0; i < 8; ++i) { z[8 * J + i] = wv[i]; zJ[8 * p + i] = wv[i]; }
             }
           } else if (lane == 0) {
             s_fail = 1;
           }
+          if (lane == 0) s_colfail[p] = ok ? 0 : 1;
+          __syncwarp();
           BA_TR(10);
-          bar_arrive(3, 32 * (kNW + 1));                           // W_J, zJ (or the failure flag) published
+          bar_arrive(kBarW + p, kCntW);                            // W_J, zJ (or the failure flag) published
+          bar_sync(kBarA + p, kCntA);                              // -A_{J+1,J} is in Asm[p] (shipped a column ago)
           if (!ok) { stop = true; break; }
+          if (J + 1 < je || handover) {
+            // ---- [L], [D]: the chain to the next diagonal tile stays inside this warp ----
+            const int pn = (J + 1) & 1;
+            bar_sync(kBarN + pn, 64);                              // -D_{J+1} (updates of columns <= J-1) is in Dnsm[pn]
+            const double2 wb = *reinterpret_cast<const double2 *>(Wsm + 64 * p + 2 * lane);
+            const double2 af = *reinterpret_cast<const double2 *>(Asm + (16 * p + 1) * 64 + 2 * lane);
+            double l0, l1;
+            dmma884(l0, l1, af.x, wb.x, 0.0, 0.0);
+            dmma884(l0, l1, af.y, wb.y, l0, l1);                   // L_{J+1,J}, C layout
+            Fsm[g * 8 + oc0] = l0; Fsm[g * 8 + oc1] = l1;          // -> operand layout through shared memory
+            double part = l0 * zJ[8 * p + 2 * q] + l1 * zJ[8 * p + 2 * q + 1];
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (q == 0 && J + 1 < NTloc) z[8 * (J + 1) + g] -= part;   // z_{J+1} -= L zJ (the panel warps skip d = 1)
+            double n0 = Dnsm[64 * pn + g * 8 + 2 * q], n1 = Dnsm[64 * pn + g * 8 + 2 * q + 1];
+            __syncwarp();
+            const double2 f1 = *reinterpret_cast<const double2 *>(Fsm + 2 * lane);
+            dmma884(n0, n1, f1.x, f1.x, n0, n1);
+            dmma884(n0, n1, f1.y, f1.y, n0, n1);                   // -D_{J+1} with the update of column J
+            if (J + 1 < je) {
+              const double dmp = dd[8 * (J + 1) + g];
+              Dsm[g * kPs + 2 * q] = (2 * q == g ? dmp : 0.0) - n0;
+              Dsm[g * kPs + 2 * q + 1] = (2 * q + 1 == g ? dmp : 0.0) - n1;
+            } else {                                               // hand-over: back to the warp of diagonal 0
+              Hsm[g * 8 + 2 * q] = n0; Hsm[g * 8 + 2 * q + 1] = n1;
+            }
+            __syncwarp();
+          }
         }
-        if (stop) break;
+        (void)stop;                                                // a failed side still meets the hand-over barriers of segment 1
+      }
+    } else if (is_panel) {
+      // =================== panel warps: L_dJ = A_dJ W_J^T for d = 1..15 (eight and seven tiles), the right-hand side
+      //                     update z_{J+d} -= L_dJ zJ, and the factor's way to global memory — while the tile warps are
+      //                     still busy with the trailing update of column J-1 ==========================================
+      const int pw = warp - kNW;
+      for (int seg = 0; seg < nsegs; ++seg) {
+        if (seg == 1) {                                            // twist hand-over (see the tile-warp branch)
+          __syncthreads();
+          cluster_sync();
+          __syncthreads();
+        }
+        const int jb = seg ? c1 : 0, je = seg ? ((side == 0 && !s_abort) ? NTloc : c1) : c1;
+        for (int J = jb; J < je; ++J) {
+          const int p = J & 1;
+          if (pw == 0) BA_TR(4);
+          bar_sync(kBarA + p, kCntA);                              // -A_{dJ} of every diagonal is in Asm[p]
+          if (pw == 0) BA_TR(5);
+          bar_sync(kBarW + p, kCntW);                              // W_J, zJ ready (or the column failed)
+          const int sf = s_colfail[p];
+          if (pw == 0) BA_TRD(6, sf);
+          if (sf) { bar_arrive(kBarP + p, kCntP); break; }         // wake the tile warps: they leave through the flag too
+          const double2 wb = *reinterpret_cast<const double2 *>(Wsm + 64 * p + 2 * lane);   // B[k][n] = -W[n][k], n = g, k = 4h + q
+          const double zq0 = zJ[8 * p + 2 * q], zq1 = zJ[8 * p + 2 * q + 1];
+          // loads, first k-step, second k-step, stores: the tiles are independent, keep them in flight together
+          double2 af[kPanelTiles];
+          double p0[kPanelTiles], p1[kPanelTiles];
+#pragma unroll
+          for (int k = 0; k < kPanelTiles; ++k) {
+            const int d = kPanelTiles * pw + 1 + k;
+            af[k] = *reinterpret_cast<const double2 *>(Asm + (16 * p + (d > 15 ? 15 : d)) * 64 + 2 * lane);
+          }
+#pragma unroll
+          for (int k = 0; k < kPanelTiles; ++k) dmma884(p0[k], p1[k], af[k].x, wb.x, 0.0, 0.0);
+#pragma unroll
+          for (int k = 0; k < kPanelTiles; ++k) dmma884(p0[k], p1[k], af[k].y, wb.y, p0[k], p1[k]);   // (-A) (-W)^T
+#pragma unroll
+          for (int k = 0; k < kPanelTiles; ++k) {
+            const int d = kPanelTiles * pw + 1 + k;
+            if (d > 15) continue;
+            double *ps = Psm + (16 * p + d) * 64 + g * 8;
+            ps[oc0] = p0[k]; ps[oc1] = p1[k];
+          }
+          double part[kPanelTiles];
+#pragma unroll
+          for (int k = 0; k < kPanelTiles; ++k) part[k] = p0[k] * zq0 + p1[k] * zq1;   // z_a -= L_aJ zJ
+#pragma unroll
+          for (int k = 0; k < kPanelTiles; ++k) part[k] += __shfl_xor_sync(0xffffffffu, part[k], 1);
+#pragma unroll
+          for (int k = 0; k < kPanelTiles; ++k) part[k] += __shfl_xor_sync(0xffffffffu, part[k], 2);
+          // z_{J+2} is read by the factor warp one column from now, with nothing but this barrier in between: d = 2 goes
+          // before the arrive (d = 1 is the factor warp's own)
+          if (pw == 0 && q == 0 && J + 2 < NTloc) z[8 * (J + 2) + g] -= part[1];
+          bar_arrive(kBarP + p, kCntP);                            // the trailing update of column J may start
+          if (pw == 0) BA_TR(7);
+          // off the critical path: the rest of the right-hand side, factor -> global (stage format), W_J -> global
+#pragma unroll
+          for (int k = 0; k < kPanelTiles; ++k) {
+            const int d = kPanelTiles * pw + 1 + k;
+            if (d > 15) continue;
+            if (J + d < NTloc) {                                   // tiles below this side's matrix are all zero
+              const int r = 8 * (J + d) + g;
+              if (q == 0 && d > 2) z[r] -= part[k];
+              double *lp = L + (size_t)r * 128 + (2 * q - 8 * d + 120);   // L(r, 8J + 2q): even offset, one 16-byte store
+              const int dl = 8 * d + g - 2 * q;
+              if (dl <= bw) *reinterpret_cast<double2 *>(lp) = make_double2(p0[k], p1[k]);
+              else if (dl - 1 <= bw) lp[1] = p1[k];
+            }
+          }
+          if (pw == kNP - 1) {
+            L[(size_t)(8 * J + (lane >> 3)) * 128 + 120 + (lane & 7)] = -Wsm[64 * p + op_idx(lane >> 3, lane & 7)];
+            L[(size_t)(8 * J + 4 + (lane >> 3)) * 128 + 120 + (lane & 7)] = -Wsm[64 * p + op_idx(4 + (lane >> 3), lane & 7)];
+          }
+        }
       }
     } else if (is_tile) {
-      // =================== tile warps: one instantiation of the column loop per warp ===========================
+      // =================== tile warps ===========================================================================
+      // Refill of diagonal d for tile row R = tile (R, R - d): the two elements of a lane sit at a fixed offset inside
+      // the tile, so their band-storage indices advance by a constant per tile row and the in-band tests are loop
+      // invariants; only "row < M" (side 0, last tile rows) is checked per row. Rows are fetched ONE COLUMN AHEAD of
+      // their use (the tile that closes diagonal 15 is next column's panel tile right away).
+      const int rstep = side ? -(8 * ld + 8) : (8 * ld + 8);
+      const int rsec = side ? -ld : 1;                              // second element: next column (side 0) / previous row (side 1)
+      auto refill_setup = [&](int d, int &ridx, bool &rin0, bool &rin1) {
+        const int dl = 8 * d + g - 2 * q;                           // row - column of the lane's first element
+        const int rl = g, cl = -8 * d + 2 * q;                      // tile row 0 (extrapolated)
+        const int r0 = side ? Mp - 1 - cl : rl, c0g = side ? Mp - 1 - rl : cl;
+        ridx = r0 * ld + c0g + off;
+        rin0 = dl >= 0 && dl <= bw;
+        rin1 = dl - 1 >= 0 && dl - 1 <= bw;
+      };
+      auto refill_fetch = [&](int R, int ridx, bool rin0, bool rin1, bool diag, double &v0, double &v1) {
+        v0 = v1 = 0.0;
+        if (R < NTloc) {
+          const bool live = side || 8 * R + g < M;                  // side 0: rows >= M are identity padding
+          const int i0 = ridx + R * rstep;
+          if (rin0 && live) v0 = __ldcg(S + i0);
+          if (rin1 && live) v1 = __ldcg(S + i0 + rsec);
+          if (diag && !live) { v0 = (2 * q == g) ? 1.0 : 0.0; v1 = (2 * q + 1 == g) ? 1.0 : 0.0; }
+        }
+      };
+      // ---- warp 0: diagonal 0. Its tiles (J+j, J+j), j = 2..15, live in registers; the tile that reaches j = 2 gets
+      //      column J's update first and goes to the factor warp (Dnsm), which owns it from there on. ----
+      auto run_diag0 = [&]() {
+        constexpr int NS = 14;                                      // slot s <-> window-relative (s + 2, s + 2)
+        double ct[NS][2], dx[2][2];                                 // dx: tiles (jb, jb), (jb+1, jb+1) at a segment start
+        {
+          double v0, v1;
+#pragma unroll
+          for (int s2 = 0; s2 < NS; ++s2) {
+            v0 = v1 = 0.0;
+            if (s2 + 2 < NTloc) load_frag(s2 + 2, s2 + 2, v0, v1);
+            ct[s2][0] = -v0; ct[s2][1] = -v1;
+          }
+          load_frag(0, 0, v0, v1); dx[0][0] = -v0; dx[0][1] = -v1;
+          v0 = v1 = 0.0;
+          if (1 < NTloc) load_frag(1, 1, v0, v1);
+          dx[1][0] = -v0; dx[1][1] = -v1;
+        }
+        int ridx; bool rin0, rin1;
+        refill_setup(0, ridx, rin0, rin1);
+        double rf[2], rn[2], pend_z = 0.0, pend_d = 0.0, pnxt_z = 0.0, pnxt_d = 0.0;
+        for (int seg = 0; seg < nsegs; ++seg) {
+          if (seg == 1) {
+            __syncthreads();
+            if (!s_fail) {                                          // the two tiles the chain holds for column c1, c1 + 1
+              dx[0][0] = Hsm[g * 8 + 2 * q]; dx[0][1] = Hsm[g * 8 + 2 * q + 1];
+              dx[1][0] = Dnsm[64 * ((c1 + 1) & 1) + g * 8 + 2 * q]; dx[1][1] = Dnsm[64 * ((c1 + 1) & 1) + g * 8 + 2 * q + 1];
+            }
+            if (side == 1 && !s_fail) {
+#pragma unroll
+              for (int t = 0; t < NS + 2; ++t) {
+                const int rl = 8 * (c1 + t) + g, cl = 8 * (c1 + t) + 2 * q;
+                double *d = XD + (size_t)(rl - 8 * c1) * 128 + (cl - 8 * c1);
+                const double t0 = t < 2 ? dx[t < 2 ? t : 0][0] : ct[t >= 2 ? t - 2 : 0][0], t1 = t < 2 ? dx[t < 2 ? t : 0][1] : ct[t >= 2 ? t - 2 : 0][1];
+                d[0] = -t0 - Aval(rl, cl);
+                d[1] = -t1 - Aval(rl, cl + 1);
+              }
+              const int i = lane;                                   // warp 0: rows 0..31 of the middle's right-hand side
+              { const int r = Mp - 1 - (8 * c1 + i); XD[16384 + i] = z[8 * c1 + i] - (r < M ? __ldcg(cv.y + r) : 0.0); }
+            }
+            if (tau == 0) gf[side] = s_fail;
+            cluster_sync();
+            if (tau == 0) s_abort = side == 0 ? (gf[1] | s_fail) : s_fail;
+            __syncthreads();
+            if (side == 0 && !s_abort) {
+#pragma unroll
+              for (int t = 0; t < NS + 2; ++t) {
+                const int r = 8 * (c1 + t) + g, c = 8 * (c1 + t) + 2 * q;
+                const double *d = XD + (size_t)(Mp - 1 - c - 8 * Jm1) * 128 + (Mp - 1 - r - 8 * Jm1);
+                if (t < 2) { dx[t < 2 ? t : 0][0] -= d[0]; dx[t < 2 ? t : 0][1] -= d[-128]; }
+                else { ct[t >= 2 ? t - 2 : 0][0] -= d[0]; ct[t >= 2 ? t - 2 : 0][1] -= d[-128]; }
+              }
+              z[8 * c1 + lane] += XD[16384 + 127 - lane];
+              bar_sync(kBarZ, 32 * kNW);                           // z of the middle complete before anybody reads it
+            }
+          }
+          const int jb = seg ? c1 : 0, je = seg ? ((side == 0 && !s_abort) ? NTloc : c1) : c1;
+          const bool handover = twist && seg == 0;
+          if (jb < je) {                                            // pipeline prologue
+            refill_fetch(jb + 16, ridx, rin0, rin1, true, rf[0], rf[1]);
+            const double dmp = dd[8 * jb + g];                      // tile (jb,jb) + damping -> factor warp
+            Dsm[g * kPs + 2 * q] = (2 * q == g ? dmp : 0.0) - dx[0][0];
+            Dsm[g * kPs + 2 * q + 1] = (2 * q + 1 == g ? dmp : 0.0) - dx[0][1];
+            bar_arrive(kBarD, 64);
+            if (jb + 1 < je || handover) {                          // tile (jb+1,jb+1), no update yet
+              Dnsm[64 * ((jb + 1) & 1) + g * 8 + 2 * q] = dx[1][0]; Dnsm[64 * ((jb + 1) & 1) + g * 8 + 2 * q + 1] = dx[1][1];
+              bar_arrive(kBarN + ((jb + 1) & 1), 64);
+            }
+            bar_arrive(kBarA + (jb & 1), kCntA);                   // (nothing to ship: keeps the barrier's count)
+          }
+          for (int J = jb; J < je; ++J) {
+            const int p = J & 1;
+            BA_TR(0);
+            if (feed.flags && J + 18 < NTloc) wait_cursor(need_of(J + 18));
+            refill_fetch(J + 17, ridx, rin0, rin1, true, rn[0], rn[1]);
+            if (feed.flags && lane < 8 && J + 18 < NTloc && 8 * (J + 18) >= 144) {
+              const int rl = 8 * (J + 18) + lane, r = side ? Mp - 1 - rl : rl;
+              pnxt_z = r < M ? __ldcg(cv.y + r) : 0.0;
+              pnxt_d = r < M ? ep + lm * __ldcg(S + Sg(r, r)) : 0.0;
+            }
+            bar_sync(kBarP + p, kCntP);                            // all panel tiles L_{dJ} are in Psm[p]
+            const int sf = s_colfail[p];
+            BA_TRD(1, sf);
+            if (sf) break;
+            const bool have_next = J + 1 < je;
+            double2 pf[16];
+#pragma unroll
+            for (int i = 2; i < 16; ++i) pf[i] = *reinterpret_cast<const double2 *>(Psm + (16 * p + i) * 64 + 2 * lane);
+            // ---- tile (J+2,J+2) first: with column J's update it goes to the factor warp ----
+            {
+              double c0 = ct[0][0], c1v = ct[0][1];
+              dmma884(c0, c1v, pf[2].x, pf[2].x, c0, c1v);
+              dmma884(c0, c1v, pf[2].y, pf[2].y, c0, c1v);
+              const bool wanted = J + 2 < je || (handover && J + 2 == je);       // the factor warp will wait for it
+              if (wanted || (handover && J + 2 == je + 1)) {
+                Dnsm[64 * (J & 1) + g * 8 + 2 * q] = c0; Dnsm[64 * (J & 1) + g * 8 + 2 * q + 1] = c1v;
+              }
+              if (wanted) bar_arrive(kBarN + (J & 1), 64);
+            }
+            if (have_next) {
+              if (feed.flags && lane < 8 && J + 17 < NTloc && 8 * (J + 17) >= 144) {
+                z[8 * (J + 17) + lane] = pend_z; dd[8 * (J + 17) + lane] = pend_d;    // rows first touched by column J + 2
+              }
+              bar_arrive(kBarA + ((J + 1) & 1), kCntA);
+            }
+            BA_TR(2);
+            // ---- the rest of diagonal 0 + slide ----
+#pragma unroll
+            for (int s2 = 1; s2 < NS; ++s2) dmma884(ct[s2][0], ct[s2][1], pf[s2 + 2].x, pf[s2 + 2].x, ct[s2][0], ct[s2][1]);
+#pragma unroll
+            for (int s2 = 1; s2 < NS; ++s2) dmma884(ct[s2 - 1][0], ct[s2 - 1][1], pf[s2 + 2].y, pf[s2 + 2].y, ct[s2][0], ct[s2][1]);
+            ct[NS - 1][0] = -rf[0]; ct[NS - 1][1] = -rf[1];
+            rf[0] = rn[0]; rf[1] = rn[1];
+            pend_z = pnxt_z; pend_d = pnxt_d;
+            BA_TR(3);
+          }
+        }
+      };
+      // ---- warps 1..8: diagonal D1 = w and, for w >= 2, diagonal D2 = 17 - w: 15 tiles, 30 DMMAs per column ----
       auto run = [&](auto d1c) {
-        constexpr int D1 = decltype(d1c)::value, D2 = 15 - D1;
-        constexpr int N1 = 16 - D1, NTL = 17;                       // tiles of diagonal D1; N1 + (16 - D2) = 17
+        constexpr int D1 = decltype(d1c)::value, D2 = D1 >= 2 ? 17 - D1 : -1;
+        constexpr int N1 = 16 - D1, N2 = D2 >= 0 ? 16 - D2 : 0, NTL = N1 + N2;
         // slot t holds window-relative tile (TJ + TD, TJ)
 #define TD(t) ((t) < N1 ? D1 : D2)
 #define TJ(t) ((t) < N1 ? (t) : (t) - N1)
@@ -294,24 +578,28 @@ __global__ void __launch_bounds__(kThreadsDg, 1) k_solve_band_diag(CallView cv, 
           if (TJ(t) + TD(t) < NTloc) load_frag(TJ(t) + TD(t), TJ(t), v0, v1);
           ct[t][0] = -v0; ct[t][1] = -v1;
         }
-        auto publish_diag = [&](int Jn) {                           // D1 == 0: tile (Jn,Jn) = ct[0] -> factor warp
-          const double dmp = dd[8 * Jn + g];
-          Dsm[g * kPs + 2 * q] = (2 * q == g ? dmp : 0.0) - ct[0][0];
-          Dsm[g * kPs + 2 * q + 1] = (2 * q + 1 == g ? dmp : 0.0) - ct[0][1];
-          bar_arrive(2, 64);
+        // the first tile of each diagonal is the next column's panel tile: ship -A to the panel warps (operand layout)
+        auto ship = [&](int Jn) {
+          double *as = Asm + 16 * (Jn & 1) * 64 + g * 8;
+          as[D1 * 64 + oc0] = ct[0][0]; as[D1 * 64 + oc1] = ct[0][1];
+          if (D2 >= 0) { as[(D2 >= 0 ? D2 : 0) * 64 + oc0] = ct[N1 < NTL ? N1 : 0][0]; as[(D2 >= 0 ? D2 : 0) * 64 + oc1] = ct[N1 < NTL ? N1 : 0][1]; }
+          bar_arrive(kBarA + (Jn & 1), kCntA);
         };
-        double pend_z = 0.0, pend_d = 0.0;                          // streaming mode: y / damping of the rows fetched last column
-        int pend_row = -1;
-        if (D1 == 0) publish_diag(0);
-        __syncwarp();
-        const int oc0 = ((2 * q) & 3) * 2 + ((2 * q) >> 2), oc1 = ((2 * q + 1) & 3) * 2 + ((2 * q + 1) >> 2);
-        const int src0 = (lane & ~3) | (q >> 1), src1 = src0 + 2;
-        bool failed = false;
-        for (int seg = 0; seg < nsegs && !failed; ++seg) {
+        int ridx[2];
+        bool rin0[2], rin1[2];
+        refill_setup(D1, ridx[0], rin0[0], rin1[0]);
+        refill_setup(D2 >= 0 ? D2 : 0, ridx[1], rin0[1], rin1[1]);
+        auto fetch_row = [&](int R, double (&rfv)[2][2]) {
+          refill_fetch(R, ridx[0], rin0[0], rin1[0], false, rfv[0][0], rfv[0][1]);
+          rfv[1][0] = rfv[1][1] = 0.0;
+          if (D2 >= 0) refill_fetch(R, ridx[1], rin0[1], rin1[1], false, rfv[1][0], rfv[1][1]);
+        };
+        double rf[2][2], rn[2][2];                                  // tile row J + 16 (in hand), J + 17 (in flight)
+        for (int seg = 0; seg < nsegs; ++seg) {
           if (seg == 1) {
             // ---- twist hand-over. Side 1: what its eliminations did to the 16 middle tile columns (window minus
             //      the untouched matrix) and to the right-hand side goes to XD in its local coordinates. Side 0 adds
-            //      it to its window and publishes the diagonal tile of column c1. ----
+            //      it to its window and restarts the pipeline at column c1. ----
             __syncthreads();
             if (side == 1 && !s_fail) {
 #pragma unroll
@@ -324,9 +612,7 @@ __global__ void __launch_bounds__(kThreadsDg, 1) k_solve_band_diag(CallView cv, 
               const int i = warp * 32 + lane;
               if (i < 128) { const int r = Mp - 1 - (8 * c1 + i); XD[16384 + i] = z[8 * c1 + i] - (r < M ? __ldcg(cv.y + r) : 0.0); }
             }
-            if (tau == 0) gf[side] = s_fail;
             cluster_sync();
-            if (tau == 0) s_abort = side == 0 ? (gf[1] | s_fail) : s_fail;
             __syncthreads();
             if (side == 0 && !s_abort) {
 #pragma unroll
@@ -338,131 +624,61 @@ __global__ void __launch_bounds__(kThreadsDg, 1) k_solve_band_diag(CallView cv, 
               }
               const int i = warp * 32 + lane;
               if (i < 128) z[8 * c1 + i] += XD[16384 + 127 - i];
-              bar_sync(1, 32 * kNW);                               // z of the middle complete before the factor warp reads it
-              if (D1 == 0) publish_diag(c1);
-              __syncwarp();
+              bar_sync(kBarZ, 32 * kNW);                           // z of the middle complete before anybody reads it
             }
           }
           const int jb = seg ? c1 : 0, je = seg ? ((side == 0 && !s_abort) ? NTloc : c1) : c1;
-          for (int J = jb; J < je; ++J) {
-            if (warp == 0) BA_TR(0);
-            const int an = J + 16;                                  // tile row entering the window for column J + 1
-            if (feed.flags) {
-              // rows of the entering tile row: complete? Then fetch their y and diagonal — into registers now, into
-              // z / dd one column later (first needed by that column's [P])
-              if (pend_row >= 0) {
-                if (warp == 0 && lane < 8) { z[pend_row + lane] = pend_z; dd[pend_row + lane] = pend_d; }
-                pend_row = -1;
-              }
-              if (an < NTloc) {
-                wait_cursor(need_of(an));
-                if (8 * an >= 128) {
-                  if (warp == 0 && lane < 8) {
-                    const int rl = 8 * an + lane, r = side ? Mp - 1 - rl : rl;
-                    pend_z = r < M ? __ldcg(cv.y + r) : 0.0;
-                    pend_d = r < M ? ep + lm * __ldcg(S + Sg(r, r)) : 0.0;
-                  }
-                  pend_row = 8 * an;
-                }
-              }
-            }
-            double rf[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-            if (an < NTloc) {                                       // tiles (an, an - d): the free ends of the two diagonals
-              load_frag(an, an - D1, rf[0][0], rf[0][1]);
-              load_frag(an, an - D2, rf[1][0], rf[1][1]);
-            }
-            if (warp == 0) BA_TR(1);
-            bar_sync(3, 32 * (kNW + 1));                           // W_J, zJ ready; every tile warp is past [U](J-1)
-            const int sf = s_fail;
-            if (warp == 0) BA_TRD(2, sf);
-            if (sf) { failed = true; break; }
-            if (warp == kNW - 1) {                                  // W_J -> global for the back substitution
-              L[(size_t)(8 * J + (lane >> 3)) * 128 + 120 + (lane & 7)] = -Wsm[op_idx(lane >> 3, lane & 7)];
-              L[(size_t)(8 * J + 4 + (lane >> 3)) * 128 + 120 + (lane & 7)] = -Wsm[op_idx(4 + (lane >> 3), lane & 7)];
-            }
-            // ---- [P] panel tiles: L_dJ = A_dJ W^T = (-A_dJ) (-W)^T ----
-            const double2 wb = *reinterpret_cast<const double2 *>(Wsm + 2 * lane);   // B[k][n] = -W[n][k], n = g, k = 4h + q
-            const double zq0 = zJ[2 * q], zq1 = zJ[2 * q + 1];
-            const int cJ = 8 * J + 2 * q;
-            auto panel = [&](const double c0, const double c1v, const int d) {
-              // C fragment (cols 2q, 2q+1 of row g) -> A fragments (col 4h + q of row g)
-              const double v00 = __shfl_sync(0xffffffffu, c0, src0), v01 = __shfl_sync(0xffffffffu, c1v, src0);
-              const double v10 = __shfl_sync(0xffffffffu, c0, src1), v11 = __shfl_sync(0xffffffffu, c1v, src1);
-              const double a0 = (q & 1) ? v01 : v00, a1 = (q & 1) ? v11 : v10;
-              double p0, p1;
-              dmma884(p0, p1, a0, wb.x, 0.0, 0.0);
-              dmma884(p0, p1, a1, wb.y, p0, p1);
-              double part = p0 * zq0 + p1 * zq1;                   // right-hand side: z_a -= L_aJ zJ
-              part += __shfl_xor_sync(0xffffffffu, part, 1);
-              part += __shfl_xor_sync(0xffffffffu, part, 2);
-              double *ps = Psm + d * 64 + g * 8;
-              ps[oc0] = p0; ps[oc1] = p1;
-              const int r = 8 * (J + d) + g;
-              if (r < 8 * NTloc) {                                 // tiles below this side's matrix are all zero
-                if (q == 0) z[r] -= part;
-                double *lp = L + Lg(r, cJ);                          // even offset in a 1 KB-aligned row: one 16-byte store
-                if (r - cJ <= bw) *reinterpret_cast<double2 *>(lp) = make_double2(p0, p1);
-                else if (r - cJ - 1 <= bw) lp[1] = p1;
-              }
-            };
-            const bool have_next = J + 1 < je;
-            if (D1 >= 1) panel(ct[0][0], ct[0][1], D1);
-            if (D1 == 1 && have_next) bar_arrive(4, 64);           // L_{J+1,J} stored: the look-ahead may start
-            panel(ct[N1][0], ct[N1][1], D2);
-            // ---- look-ahead: tile (J+1,J+1) only needs L_{J+1,J} ----
-            if (D1 == 0 && have_next) {
-              bar_sync(4, 64);
-              const double2 f1 = *reinterpret_cast<const double2 *>(Psm + 64 + 2 * lane);
-              double c0 = ct[1][0], c1v = ct[1][1];
-              dmma884(c0, c1v, f1.x, f1.x, c0, c1v);
-              dmma884(c0, c1v, f1.y, f1.y, c0, c1v);
-              ct[0][0] = c0; ct[0][1] = c1v;
-              publish_diag(J + 1);
-            }
-            if (warp == 0) BA_TR(3);
-            bar_sync(1, 32 * kNW);                                 // all panel tiles (and z updates) of column J done
-            if (warp == 0) BA_TRD(4, Psm[64]);
-            // ---- [U] trailing update + slide: tile[j-1] <- L_{j+d} L_j^T + tile[j], two passes of independent DMMAs ----
-            {
-              double2 pf[16];
-#pragma unroll
-              for (int i = 1; i < 16; ++i) pf[i] = *reinterpret_cast<const double2 *>(Psm + i * 64 + 2 * lane);
-#pragma unroll
-              for (int t = 0; t < NTL; ++t) {
-                if (TJ(t) >= 1) {
-                  if (D1 == 0 && t == 1) { if (!have_next) dmma884(ct[t][0], ct[t][1], pf[TJ(t) + TD(t)].x, pf[TJ(t)].x, ct[t][0], ct[t][1]); }
-                  else dmma884(ct[t][0], ct[t][1], pf[TJ(t) + TD(t)].x, pf[TJ(t)].x, ct[t][0], ct[t][1]);
-                }
-              }
-#pragma unroll
-              for (int t = 0; t < NTL; ++t) {
-                if (TJ(t) >= 1) {
-                  if (D1 == 0 && t == 1) { if (!have_next) dmma884(ct[t - 1][0], ct[t - 1][1], pf[TJ(t) + TD(t)].y, pf[TJ(t)].y, ct[t][0], ct[t][1]); }
-                  else dmma884(ct[t - 1][0], ct[t - 1][1], pf[TJ(t) + TD(t)].y, pf[TJ(t)].y, ct[t][0], ct[t][1]);
-                }
-              }
-              ct[N1 - 1][0] = -rf[0][0]; ct[N1 - 1][1] = -rf[0][1];
-              ct[NTL - 1][0] = -rf[1][0]; ct[NTL - 1][1] = -rf[1][1];
-            }
-            if (warp == 0) BA_TR(5);
+          if (jb < je) {                                            // pipeline prologue: column jb's A tiles
+            fetch_row(jb + 16, rf);
+            ship(jb);
           }
-          if (pend_row >= 0) {
-            if (warp == 0 && lane < 8) { z[pend_row + lane] = pend_z; dd[pend_row + lane] = pend_d; }
-            pend_row = -1;
+          for (int J = jb; J < je; ++J) {
+            const int p = J & 1;
+            // tile row J + 17 (one column ahead): in streaming mode its Schur units must be complete first
+            if (feed.flags && J + 18 < NTloc) wait_cursor(need_of(J + 18));
+            fetch_row(J + 17, rn);
+            bar_sync(kBarP + p, kCntP);                            // all panel tiles L_{dJ} are in Psm[p]
+            if (s_colfail[p]) break;
+            const bool have_next = J + 1 < je;
+            double2 pf[16];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) pf[i] = *reinterpret_cast<const double2 *>(Psm + (16 * p + i) * 64 + 2 * lane);
+            // ---- the tiles that become next column's panel tiles first: tile[0] <- L_{1+d} L_1^T + tile[1] ----
+#pragma unroll
+            for (int t = 0; t < NTL; ++t) {
+              if (TJ(t) == 1) {
+                dmma884(ct[t][0], ct[t][1], pf[1 + TD(t)].x, pf[1].x, ct[t][0], ct[t][1]);
+                dmma884(ct[t - 1][0], ct[t - 1][1], pf[1 + TD(t)].y, pf[1].y, ct[t][0], ct[t][1]);
+              }
+            }
+            if (N2 == 1) { ct[NTL - 1][0] = -rf[1][0]; ct[NTL - 1][1] = -rf[1][1]; }   // diagonal 15: the entering tile IS the next panel tile
+            if (have_next) ship(J + 1);
+            // ---- the rest of the trailing update + slide: tile[j-1] <- L_{j+d} L_j^T + tile[j], two passes ----
+#pragma unroll
+            for (int t = 0; t < NTL; ++t)
+              if (TJ(t) >= 2) dmma884(ct[t][0], ct[t][1], pf[TJ(t) + TD(t)].x, pf[TJ(t)].x, ct[t][0], ct[t][1]);
+#pragma unroll
+            for (int t = 0; t < NTL; ++t)
+              if (TJ(t) >= 2) dmma884(ct[t - 1][0], ct[t - 1][1], pf[TJ(t) + TD(t)].y, pf[TJ(t)].y, ct[t][0], ct[t][1]);
+            ct[N1 - 1][0] = -rf[0][0]; ct[N1 - 1][1] = -rf[0][1];
+            if (N2 >= 2) { ct[NTL - 1][0] = -rf[1][0]; ct[NTL - 1][1] = -rf[1][1]; }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { rf[k][0] = rn[k][0]; rf[k][1] = rn[k][1]; }
           }
         }
 #undef TD
 #undef TJ
       };
       switch (warp) {
-        case 0: run(std::integral_constant<int, 0>{}); break;
+        case 0: run_diag0(); break;
         case 1: run(std::integral_constant<int, 1>{}); break;
         case 2: run(std::integral_constant<int, 2>{}); break;
         case 3: run(std::integral_constant<int, 3>{}); break;
         case 4: run(std::integral_constant<int, 4>{}); break;
         case 5: run(std::integral_constant<int, 5>{}); break;
         case 6: run(std::integral_constant<int, 6>{}); break;
-        default: run(std::integral_constant<int, 7>{}); break;
+        case 7: run(std::integral_constant<int, 7>{}); break;
+        default: run(std::integral_constant<int, 8>{}); break;
       }
     }
     __syncthreads();
@@ -534,7 +750,7 @@ __global__ void __launch_bounds__(kThreadsDg, 1) k_solve_band_diag(CallView cv, 
           }
           xsol[8 * J + tau] = s0 + s1;
         }
-        if (tau < 160) bar_sync(5, 160);
+        if (tau < 160) bar_sync(kBarX, 160);
         if (tau >= 32 && tau < 32 + 120) {
           const int xcol = tau - 32, c = 8 * (J - 15) + xcol;
           if (c >= 0) {
@@ -582,7 +798,7 @@ __global__ void __launch_bounds__(kThreadsDg, 1) k_solve_band_diag(CallView cv, 
 
 size_t solve_diag_smem_bytes(int M) {
   const int Mp = ((M + 7) / 8) * 8;
-  return ((size_t)2 * Mp + 16 * 64 + 8 * kPs + 64 + 8 + kBackStages * (8 * 128)) * sizeof(double);
+  return ((size_t)2 * Mp + 4 * 16 * 64 + 8 * kPs + 2 * 64 + 2 * 8 + 4 * 64 + kBackStages * (8 * 128)) * sizeof(double);
 }
 
 int launch_solve_band_diag(const CallView &cv, int allow_retry, double *scratch, const SolveFeed &feed, cudaStream_t s) {
@@ -601,7 +817,7 @@ int launch_solve_band_diag(const CallView &cv, int allow_retry, double *scratch,
   BA_CUDA(cudaMemsetAsync(gfl, 0, 8 * sizeof(int), s));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(twist ? 2 : 1);
-  cfg.blockDim = dim3(kThreadsDg);
+  cfg.blockDim = dim3(kHwThreadsDg);
   cfg.dynamicSmemBytes = solve_diag_smem_bytes(cv.M);
   cfg.stream = s;
   cudaLaunchAttribute at[1];

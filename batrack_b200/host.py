@@ -33,9 +33,11 @@ class HostBA:
         self._keep = []
 
     def submit(self, poses, patches, patches_monodisp, intrinsics, targets_2d, weights, lmbda, bounds, poses_out,
-               patches_out, ep=100.0, fixedp=1, structure_only=False, loss='trivial', alpha=0.5):
+               patches_out, ep=100.0, fixedp=1, structure_only=False, loss='trivial', alpha=0.5, group=None):
         """Enqueue one step on the current CUDA stream and return at once. Inputs must stay unchanged and outputs
-        are valid only after `sync()`."""
+        are valid only after `sync()`. With `group` (keyframe-sharded graph) the step is staged, assembled,
+        all-reduced over the group and solved through ba_stage_host_async / ba_assemble / ba_solve_update /
+        ba_unstage_host_async."""
         if loss not in _capi.LOSS_IDS:
             raise NotImplementedError(loss)
         info = self.plan.info
@@ -62,9 +64,22 @@ class HostBA:
         p.poses_out = _host_f32("poses_out", poses_out, (1, N, 7)).data_ptr()
         p.patches_out = _host_f32("patches_out", patches_out, (1, NM, 3, 1, 1)).data_ptr()
         dev = self.plan.device
+        L = _capi.lib()
         with torch.cuda.device(dev):
-            _capi.check(_capi.lib().ba_step_host_async(self.plan.handle, C.byref(p), _capi.stream_ptr(dev)),
-                        "ba_step_host_async")
+            st = _capi.stream_ptr(dev)
+            if group is None:
+                _capi.check(L.ba_step_host_async(self.plan.handle, C.byref(p), st), "ba_step_host_async")
+            else:
+                import torch.distributed as dist
+                from .ba import ensure_sharded_layout
+                ensure_sharded_layout(self.plan, group)
+                pd = _capi.BaProblem()
+                _capi.check(L.ba_stage_host_async(self.plan.handle, C.byref(p), C.byref(pd), st), "ba_stage_host_async")
+                _capi.check(L.ba_assemble(self.plan.handle, C.byref(pd), st), "ba_assemble")
+                if not structure_only and self.plan.layout_n_total - int(fixedp) > 0:
+                    dist.all_reduce(self.plan.reduced_system(), op=dist.ReduceOp.SUM, group=group)
+                _capi.check(L.ba_solve_update(self.plan.handle, C.byref(pd), st), "ba_solve_update")
+                _capi.check(L.ba_unstage_host_async(self.plan.handle, C.byref(p), C.byref(pd), st), "ba_unstage_host_async")
 
     def sync(self, block=True):
         """Order the current stream after every submitted step's download; block=True also waits on the host."""

@@ -1,5 +1,5 @@
 """SE3 slice of the reference's `lietorch_backends` pybind module, same call convention:
-`fn(group_id, *contiguous 2-D float32 CUDA tensors) -> tensor`
+`fn(group_id, *contiguous 2-D float32 / float64 CUDA tensors) -> tensor`
 (main/backend/lietorch/src/lietorch.cpp:286-316). Group ids as in lietorch/groups.py:236-290; only
 SE3 (3) is on BA-Track's BA path, the other groups and all *_backward entry points are out of scope
  and raise. Every call launches a hand-written kernel from libbatrack_ba.so on
@@ -17,13 +17,15 @@ def _run(name, gid, out_cols, X, *others):
         raise NotImplementedError(f"lietorch_backends.{name}: only SE3 (group id 3) is built, got {gid}")
     ts = (X,) + others
     for i, t in enumerate(ts):
-        _capi.require_cuda_f32(f"{name} arg{i}", t)
+        _capi.require_cuda_float(f"{name} arg{i}", t)
+        if t.dtype != X.dtype:
+            raise TypeError(f"{name}: mixed dtypes {[x.dtype for x in ts]}")
         if t.dim() != 2 or t.shape[0] != X.shape[0]:
             raise RuntimeError(f"{name}: expected 2-D tensors with equal batch, got {[tuple(x.shape) for x in ts]}")
     B = X.shape[0]
-    out = torch.empty((B, out_cols), dtype=torch.float32, device=X.device)
+    out = torch.empty((B, out_cols), dtype=X.dtype, device=X.device)
     with torch.cuda.device(X.device):
-        fn = getattr(_capi.lib(), "se3_" + name)
+        fn = getattr(_capi.lib(), ("se3d_" if X.dtype == torch.float64 else "se3_") + name)   # dispatch.h:37-45
         rc = fn(*[_capi.ptr(t) for t in ts], _capi.ptr(out), B, _capi.stream_ptr(X.device))
     _capi.check(rc, name)
     return out

@@ -187,12 +187,40 @@ def davis_like_update(dev, reps=20):
             "ms_per_update": timed(update), "ms_per_update_fused_call": timed(update_fused)}
 
 
+def check_parity(workload, prob, d, ba, SE3, world, dev):
+    """One step from the initial state against the committed fp64 result of the sparse oracle (iteration 1 of
+    tests/golden/<workload>_*_sparse64.npz, tests/golden/make_golden_large.py). Sharded runs first put the ranks'
+    disparity updates together (every rank moves its own tracks only; poses are replicated)."""
+    import torch.distributed as dist
+    G, p = ba(SE3(d["poses"]), d["patches"], d)
+    poses = G.data[0].double()
+    disp = p[0, :, 2, 0, 0].double()
+    if world > 1:
+        base = d["patches"][0, :, 2, 0, 0].clamp(1e-3, 10.0).double()
+        delta = disp - base                       # exactly zero on the patches of the other ranks
+        dist.all_reduce(delta, op=dist.ReduceOp.SUM)
+        disp = base + delta
+        pm = poses.clone()
+        dist.all_reduce(pm, op=dist.ReduceOp.MAX)     # replicated solve: identical on every rank
+        rank_spread = float((pm - poses).abs().max())
+    else:
+        rank_spread = 0.0
+    name = {"cfg3": "cfg3_x10_sparse64.npz", "cfg5": "cfg5_x2_sparse64.npz"}[workload]
+    z = np.load(os.path.join(ROOT, "tests", "golden", name))
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    return {"poses": rel(poses.cpu().numpy(), z["poses"][0]), "disps": rel(disp.cpu().numpy(), z["disps"][0].astype(np.float64)),
+            "pose_spread_over_ranks": rank_spread, "tolerance": 1e-4,
+            "against": f"tests/golden/{name} iteration 1 (sparse fp64 oracle)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5"],
+                    help="cfg3 = the headline graph (BASELINE.json configs[2]); cfg5 = the 1024-keyframe graph of configs[4]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="only warm-up + timed steps (for runs under ncu)")
     args = ap.parse_args()
@@ -205,10 +233,15 @@ def main():
         os.environ.setdefault("BA_STREAM", "0")
     if args.warmup < 3:
         args.warmup = 3
+    wl = args.workload
+    metric = METRIC if wl == "cfg3" else "BA iterations/sec (1024 KF, 256k tracks)"
+    workload = WORKLOAD if wl == "cfg3" else WORKLOAD.replace("cfg3: synthetic 256-KF / 65536-track / 1245184-edge",
+                                                               "cfg5: synthetic 1024-KF / 262144-track / 4980736-edge")
 
     import torch.distributed as dist
     from batrack_b200 import _capi, synth
     from batrack_b200.ba import BA_rgbd_droid
+    from batrack_b200.host import HostBA
     from batrack_b200.lietorch import SE3
     from batrack_b200.plan import Plan
 
@@ -218,10 +251,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     group = dist.group.WORLD if world > 1 else None
 
-    n_kf = synth.CONFIGS["cfg3"][0]
+    n_kf = synth.CONFIGS[wl][0]
     lo, hi = (n_kf * rank) // world, (n_kf * (rank + 1)) // world
-    prob = synth.make_config("cfg3", kf_lo=lo, kf_hi=hi)
-    E_local, N, NM = prob.E, prob.poses.shape[0], prob.patches.shape[0]
+    prob = synth.make_config(wl, kf_lo=lo, kf_hi=hi)
+    N, NM = prob.poses.shape[0], prob.patches.shape[0]
 
     # pinned host copies (e2e) and device-resident copies (value)
     host = {k: v.pin_memory() for k, v in prob.as_torch().items()}
@@ -263,6 +296,10 @@ def main():
         step(k)
     barrier()
 
+    # ---- parity of this very configuration (sharding included) against the fp64 oracle's committed result ----
+    parity = None if args.profile else check_parity(wl, prob, d, ba, SE3, world, dev)
+    barrier()
+
     # ---- value: device-resident inputs, per-step CUDA events, L2 flushed between steps ----
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = _capi.launch_count()
@@ -299,116 +336,100 @@ def main():
     plan.enable_timing(False)
     barrier()
 
-    # ---- e2e: host (pinned) buffers in, host buffers out, copies inside the timed region ----
+    # ---- e2e: the host-buffer C ABI (include/batrack_ba.h): pinned HOST arrays in, pinned HOST arrays out, every step ----
     h2d_keys = ("poses", "patches", "patches_monodisp", "intrinsics", "targets_2d", "weights")
     h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in h2d_keys)
-    out_pose = torch.empty((1, N, 7), dtype=torch.float32).pin_memory()
-    out_patch = torch.empty((1, NM, 3, 1, 1), dtype=torch.float32).pin_memory()
-    d2h_bytes = out_pose.numel() * 4 + out_patch.numel() * 4
+    outs = [(torch.empty((1, N, 7), dtype=torch.float32).pin_memory(), torch.empty((1, NM, 3, 1, 1), dtype=torch.float32).pin_memory())
+            for _ in range(2)]
+    d2h_bytes = outs[0][0].numel() * 4 + outs[0][1].numel() * 4
+    hba = HostBA(plan)
+    kw = dict(ep=prob.ep, fixedp=prob.fixedp, structure_only=False, loss=prob.loss, alpha=prob.alpha, group=group)
 
-    def e2e_step():
-        src = {k: host[k].to(dev, non_blocking=True) for k in h2d_keys}
-        G, p = ba(SE3(src["poses"]), src["patches"], src)
-        out_pose.copy_(G.data, non_blocking=True)
-        out_patch.copy_(p, non_blocking=True)
+    def submit(poses_h, patches_h, out):
+        hba.submit(poses_h, patches_h, host["patches_monodisp"], host["intrinsics"], host["targets_2d"], host["weights"],
+                   prob.lmbda, prob.bounds, out[0], out[1], **kw)
 
-    def timed_e2e(fn, n, fence=None, flush_each=True):
-        for _ in range(3):
-            fn()
-        if fence:
-            fence()
-        barrier()
-        if flush_each:      # one event pair per step, L2 flushed outside the pairs
-            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
-            w0 = time.time()
-            for k in range(n):
-                flush.zero_()
-                evs[k][0].record()
-                fn()
-                evs[k][1].record()
-            barrier()
-            windows.append((w0, time.time()))
-            ms = sum(a.elapsed_time(b) for a, b in evs)
-        else:               # pipelined: one event pair around all n steps (copies of step k+1 overlap step k)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            flush.zero_()
-            barrier()
-            w0 = time.time()
-            a.record()
-            for k in range(n):
-                fn()
-            fence()
-            b.record()
-            barrier()
-            windows.append((w0, time.time()))
-            ms = a.elapsed_time(b)
+    def max_over_ranks(ms):
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t[0])
-        return 1e3 * n / ms
+            return float(t[0])
+        return ms
 
     n_e2e = min(args.steps, 100)
-    e2e_serial = timed_e2e(e2e_step, n_e2e)
-    if world == 1:
-        # the host-buffer C ABI (ba_step_host_async): double-buffered staging, copy streams owned by the library
-        from batrack_b200.host import HostBA
-        hba = HostBA(plan)
 
-        def e2e_host_step():
-            hba.submit(host["poses"], host["patches"], host["patches_monodisp"], host["intrinsics"], host["targets_2d"],
-                       host["weights"], prob.lmbda, prob.bounds, out_pose, out_patch, ep=prob.ep, fixedp=prob.fixedp,
-                       structure_only=False, loss=prob.loss, alpha=prob.alpha)
+    def e2e_dependent(n):
+        """What a host-side caller iterating BA does: step k+1 consumes the HOST results of step k (poses, patches), so
+        nothing of step k+1 can start before step k's download has finished; all six float inputs go up every step."""
+        cur = (host["poses"], host["patches"])
+        for k in range(3):
+            submit(cur[0], cur[1], outs[k & 1]); hba.sync(block=True); cur = outs[k & 1]
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        a.record()
+        cur = (host["poses"], host["patches"])
+        for k in range(n):
+            if k % LM_ITERS == 0:
+                cur = (host["poses"], host["patches"])
+            submit(cur[0], cur[1], outs[k & 1])
+            hba.sync(block=True)                       # the next step reads these host arrays
+            cur = outs[k & 1]
+        b.record()
+        barrier()
+        windows.append((w0, time.time()))
+        return 1e3 * n / max_over_ranks(a.elapsed_time(b))
 
-        e2e_val = timed_e2e(e2e_host_step, n_e2e, fence=lambda: hba.sync(block=False), flush_each=False)
+    def e2e_pipelined(n):
+        """Independent steps (e.g. many windows in flight): the upload of step k+1 and the download of step k-1 overlap
+        the kernels of step k (the library's copy streams, two staging slots)."""
+        for k in range(3):
+            submit(host["poses"], host["patches"], outs[k & 1])
         hba.sync(block=True)
-        e2e_note = ("ba_step_host_async (C ABI, include/batrack_ba.h): pinned HOST float inputs -> device staging slot "
-                    "(library's upload stream) -> BA step -> pinned HOST outputs (download stream), every step; uploads of "
-                    "step k+1 overlap the kernels of step k; one CUDA-event pair around all steps; ii/jj/kk and the topology "
-                    "plan stay resident (they change only when the SLAM graph changes)")
-    else:
-        # sharded: the same double-buffered upload around BA_rgbd_droid(group=...) (assemble -> NCCL all-reduce of
-        # [S | y] -> solve + update), copy stream and events managed here
-        copy_stream = torch.cuda.Stream(device=dev)
-        slots, ev_in, ev_done = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
-        seq = {"up": 0, "run": 0}
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        a.record()
+        for k in range(n):
+            submit(host["poses"], host["patches"], outs[k & 1])
+        hba.sync(block=False)
+        b.record()
+        barrier()
+        windows.append((w0, time.time()))
+        return 1e3 * n / max_over_ranks(a.elapsed_time(b))
 
-        def upload():
-            k = seq["up"]
-            sl = k & 1
-            with torch.cuda.stream(copy_stream):
-                if k >= 2:
-                    copy_stream.wait_event(ev_done[sl])
-                slots[sl] = {key: host[key].to(dev, non_blocking=True) for key in h2d_keys}
-                ev_in[sl].record(copy_stream)
-            seq["up"] = k + 1
+    def e2e_cold(n_jobs):
+        """A new graph every LM_ITERS iterations: indices uploaded (int64, as the caller holds them), topology plan built,
+        then LM_ITERS dependent host-buffer steps — all inside the timed region."""
+        t_ms = 0.0
+        for j in range(n_jobs + 1):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            idx = [host[k].to(dev, non_blocking=True) for k in ("ii", "jj", "kk")]
+            pl2 = Plan(*idx, N, NM)
+            if world > 1:
+                pl2.set_layout(n_total, bwb)
+            h2 = HostBA(pl2)
+            cur = (host["poses"], host["patches"])
+            for k in range(LM_ITERS):
+                h2.submit(cur[0], cur[1], host["patches_monodisp"], host["intrinsics"], host["targets_2d"], host["weights"],
+                          prob.lmbda, prob.bounds, outs[k & 1][0], outs[k & 1][1], **kw)
+                h2.sync(block=True)
+                cur = outs[k & 1]
+            b.record()
+            barrier()
+            if j > 0:                                   # job 0 warms the allocator pool
+                t_ms += a.elapsed_time(b)
+            del h2, pl2
+        return 1e3 * n_jobs * LM_ITERS / max_over_ranks(t_ms)
 
-        def e2e_pipe_step():
-            k = seq["run"]
-            sl = k & 1
-            if seq["up"] <= k:
-                upload()
-            upload()                                   # next step's inputs go up while this step computes
-            cur = torch.cuda.current_stream()
-            cur.wait_event(ev_in[sl])
-            src = slots[sl]
-            for t in src.values():
-                t.record_stream(cur)
-            G, p = ba(SE3(src["poses"]), src["patches"], src)
-            out_pose.copy_(G.data, non_blocking=True)
-            out_patch.copy_(p, non_blocking=True)
-            ev_done[sl].record(cur)
-            seq["run"] = k + 1
+    e2e_val = e2e_dependent(n_e2e)
+    e2e_pipe = e2e_pipelined(n_e2e)
+    e2e_cold_val = e2e_cold(3)
+    idx_bytes = sum(host[k].numel() * 8 for k in ("ii", "jj", "kk"))
 
-        def fence():
-            torch.cuda.current_stream().wait_stream(copy_stream)
-
-        e2e_val = timed_e2e(e2e_pipe_step, n_e2e, fence=fence, flush_each=False)
-        e2e_note = ("pinned HOST float inputs -> device (copy stream, double-buffered: the upload of step k+1 overlaps step k) "
-                    "-> BA_rgbd_droid(group=...) -> pinned HOST outputs, every step; one CUDA-event pair around all steps; "
-                    "ii/jj/kk and the topology plan stay resident")
-
-    # ---- cold call: index upload + topology plan + one step (what the first call on a new graph costs) ----
+    # ---- cold call: index upload + topology plan (what the first call on a new graph costs) ----
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     idx = [host[k].to(dev, non_blocking=True) for k in ("ii", "jj", "kk")]
@@ -432,7 +453,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    full = synth.make_config("cfg3") if world > 1 else prob
+    full = synth.make_config(wl) if world > 1 else prob
     alg = algorithmic_bytes(full, n_free)
     edge_ms = stages.get("edge_pass", 0.0)
     alg_rank = alg / world                       # each rank streams its shard of the edges
@@ -442,40 +463,67 @@ def main():
     except Exception:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_rank / (edge_ms * 1e-3) / 1e9 if edge_ms > 0 else None
-    traffic = None
-    try:        # DRAM bytes of the same kernel from the committed ncu --set full capture (N = 1 only)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_edge_pass_v2"]
-        traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if world == 1 else None
+    traffic, prof = None, {}
+    try:        # DRAM bytes / pipe utilisation of the kernels from the committed ncu --set full captures (N = 1 only)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        tr = prof["k_edge_pass_v2"]
+        traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if (world == 1 and wl == "cfg3") else None
     except Exception:
         pass
     tot = sum(stages.values()) or 1.0
+    M, bw = 6 * n_free, 6 * bwb + 5
+    solve_ms = stages.get("solve", 0.0)
+    solve_flops = float(M) * bw * bw                                    # band Cholesky: M * bw^2
     out = {
-        "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric, "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "keyframes": n_kf, "tracks": int(np.unique(full.kk).shape[0]), "edges": full.E,
+        "config": {"workload": workload, "keyframes": n_kf, "tracks": int(np.unique(full.kk).shape[0]), "edges": full.E,
                    "free_poses": n_free, "sharding": f"keyframe windows over {world} rank(s), one NCCL all-reduce of [S|y] per step"
-                   if world > 1 else "none", "l2": "256 MiB buffer written between timed steps",
+                   if world > 1 else "none", "l2": "256 MiB buffer written between timed steps of `value`; the e2e legs do not flush",
                    "reduced_system": "band" if plan.info.banded else "dense", "block_bandwidth": bwb,
+                   "solver": "fp64 DMMA band Cholesky, diagonal tile ownership, 2-CTA twist",
+                   "schur": "tcgen05 kind::tf32 (3xTF32, fp64 read-back)" if plan.get_option("schur") == 0 else "SIMT fp32",
                    "plan": {"groups": plan.info.n_groups, "chunks": plan.info.n_chunks, "perm_identity": plan.info.perm_identity,
                             "build_ms_cold": plan_ms}},
         "clocks": clocks,
+        "parity": parity,
         "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "steps": n_e2e, "note": e2e_note, "serial_value": e2e_serial,
-                "serial_note": "same copies on ONE stream around BA_rgbd_droid (no overlap), per-step events, L2 flushed"},
+                "steps": n_e2e,
+                "note": "host-buffer C ABI (ba_step_host_async / ba_host_sync; sharded: ba_stage_host_async + ba_assemble + NCCL "
+                        "all-reduce + ba_solve_update + ba_unstage_host_async): every step uploads its six float inputs from "
+                        "pinned HOST arrays and downloads poses + patches to pinned HOST arrays; steps are DEPENDENT (step k+1 "
+                        "reads the host results of step k, state reset every 10), so no copy overlaps a kernel; one CUDA-event "
+                        "pair around all steps; ii/jj/kk and the topology plan stay resident (they change when the SLAM graph "
+                        "changes: see cold_value); L2 not flushed",
+                "pipelined_value": e2e_pipe,
+                "pipelined_note": "independent steps: upload of step k+1 / download of step k-1 overlap the kernels of step k",
+                "cold_value": e2e_cold_val,
+                "cold_note": f"a new graph every {LM_ITERS} iterations: + {idx_bytes} B of int64 indices uploaded and the topology "
+                             f"plan built once per {LM_ITERS} dependent steps, inside the timed region"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "k_edge_pass_v2 (residual + Jacobian + per-track reduction, lane per track)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "algorithmic_bytes": alg_rank, "kernel_ms": edge_ms, "peak_source": peak_src},
+        "roofline_solve": {"kernel": "k_solve_band_diag (the dominant kernel of the step)", "bound": "fp64 dependent chain / DMMA pipe",
+                           "flops": solve_flops, "kernel_ms": solve_ms,
+                           "achieved": solve_flops / (solve_ms * 1e-3) / 1e12 if solve_ms > 0 else None, "unit": "TFLOP/s",
+                           "peak": 37.0, "peak_source": "fp64 DFMA = DMMA peak measured with tools/microbench.cu (profiles/r01_microbench.txt)",
+                           "frac": solve_flops / (solve_ms * 1e-3) / 1e12 / 37.0 if solve_ms > 0 else None,
+                           "sms_used": 2, "dmma_pipe_pct_on_its_sms": prof.get("k_solve_band_diag", {}).get("fp64_pipe_pct"),
+                           "note": "with the streaming hand-over `solve` is the part of the solver left after the Schur kernel ended"},
         "kernels": {k: {"ms": v, "share": v / tot} for k, v in stages.items()},
     }
-    if world == 1:
+    if world == 1 and wl == "cfg3":
         out["other_workloads"] = {"davis_like_window": davis_like_update(dev)}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and wl == "cfg3":
         out["cpu_baseline"] = cpu_baseline(prob)
     print(json.dumps(out))
+    bad = parity is not None and (parity["poses"] > 1e-4 or parity["disps"] > 1e-4)
     if world > 1:
         dist.destroy_process_group()
+    if bad:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -109,6 +109,8 @@ int ba_plan_set_layout(BaPlan *plan, int32_t n_total, int32_t block_bandwidth);
 #define BA_OPT_SPIN_CAP 6        /* give-up bound of the streaming solver's waits, in 40 ns sleeps (default 65536 ~ 3 ms) */
 #define BA_OPT_SOLVER_TRACE 7    /* 1: the band solver records per-column clock stamps (ba_plan_read_trace) */
 #define BA_OPT_SCHUR 8           /* 0 (default): tcgen05 tensor-core Schur kernel where it applies; 1: SIMT kernel */
+#define BA_OPT_SCHUR_ACC 9       /* chunks of 32 tracks the tensor-core Schur kernel accumulates in TMEM (fp32) before the fp64
+                                    read-back: 1..8, default 2 */
 int ba_plan_set_option(BaPlan *plan, int32_t key, int32_t value);
 int ba_plan_get_option(const BaPlan *plan, int32_t key, int32_t *value);
 /* Copies the solver trace of the last traced solve to the host: n_values int64 clock stamps
@@ -182,8 +184,13 @@ int ba_plan_last_timing(BaPlan *plan, float *ms_out /* host, BA_N_STAGES floats 
  *                       run and the host outputs are valid only after ba_host_sync.
  *   ba_host_sync        order `stream` after the download of every step submitted so far; block != 0 also waits
  *                       on the host.
- *   ba_step_host        one synchronous step (= async + blocking sync). */
+ *   ba_step_host        one synchronous step (= async + blocking sync).
+ *   ba_stage_host_async / ba_unstage_host_async   the two halves of ba_step_host_async for callers that put their own
+ *                       launches between them — a sharded caller runs ba_assemble, its all-reduce of the reduced
+ *                       system and ba_solve_update on the device-side problem `prob_dev` that staging returns. */
 int ba_step_host_async(BaPlan *plan, const BaProblem *prob_host, void *stream);
+int ba_stage_host_async(BaPlan *plan, const BaProblem *prob_host, BaProblem *prob_dev, void *stream);
+int ba_unstage_host_async(BaPlan *plan, const BaProblem *prob_host, const BaProblem *prob_dev, void *stream);
 int ba_host_sync(BaPlan *plan, void *stream, int block);
 int ba_step_host(BaPlan *plan, const BaProblem *prob_host, void *stream);
 
@@ -194,6 +201,23 @@ int ba_reproject(const float *poses, const float *patches, const float *intrinsi
                  const int64_t *ii, const int64_t *jj, const int64_t *kk, int64_t n_edges,
                  int32_t n_poses, int32_t n_patches, int32_t tonly, float *coords, float *valid,
                  void *stream);
+
+/* transform() with every optional output of projective_ops.py:54-105: coords [E, depth ? 3 : 2] (the third channel is
+ * the inverse depth of proj(depth=True), :47-50), valid [E] or NULL, and the analytic Jacobians Ji, Jj [E,2,6] and
+ * Jz [E,2] of :72-100 (any of them may be NULL). */
+int ba_transform(const float *poses, const float *patches, const float *intrinsics,
+                 const int64_t *ii, const int64_t *jj, const int64_t *kk, int64_t n_edges,
+                 int32_t n_poses, int32_t n_patches, int32_t tonly, int32_t depth, float *coords, float *valid,
+                 float *Ji, float *Jj, float *Jz, void *stream);
+/* point_cloud (projective_ops.py:107-109): out[k] = T_ix[k]^-1 * iproj(patch k), [n,4] homogeneous (x, y, z, inverse depth) */
+int ba_point_cloud(const float *poses, const float *patches, const float *intrinsics, const int64_t *ix,
+                   int64_t n_points, int32_t n_poses, float *out, void *stream);
+/* back_proj (projective_ops.py:129-152): xy [B,n,2], depth [B,n], intrinsics [B,4], c2w [B,4,4] or NULL -> P [B,n,4] */
+int ba_back_proj(const float *xy, const float *depth, const float *intrinsics, const float *c2w, int32_t B,
+                 int64_t n, float *P, void *stream);
+/* proj_to_frames (projective_ops.py:154-176): P [B,n,4], intrinsics [B,S,4], w2c [B,S,4,4] -> xy [B,S,n,2] */
+int ba_proj_to_frames(const float *P, const float *intrinsics, const float *w2c, int32_t B, int32_t S, int64_t n,
+                      float *xy, void *stream);
 
 /* ---- SE3 forward ops (lietorch_backends, group id 3) ---------------------------------------- */
 /* All arrays contiguous [B,7] / [B,6] / [B,4] float32 device buffers. */
@@ -206,6 +230,18 @@ int se3_adjT(const float *X, const float *a, float *b, int64_t B, void *stream);
 int se3_act(const float *X, const float *p, float *q, int64_t B, void *stream);   /* lietorch.cpp:185 */
 int se3_act4(const float *X, const float *p, float *q, int64_t B, void *stream);  /* lietorch.cpp:214 */
 int se3_as_matrix(const float *X, float *T, int64_t B, void *stream);             /* lietorch.cpp:258 */
+
+/* The same nine ops in double precision (the reference dispatches float and double, lietorch/include/dispatch.h:37-45;
+ * its identity tests run in fp64, lietorch/run_tests.py:16-52). */
+int se3d_expm(const double *a, double *X, int64_t B, void *stream);
+int se3d_logm(const double *X, double *a, int64_t B, void *stream);
+int se3d_inv(const double *X, double *Y, int64_t B, void *stream);
+int se3d_mul(const double *X, const double *Y, double *Z, int64_t B, void *stream);
+int se3d_adj(const double *X, const double *a, double *b, int64_t B, void *stream);
+int se3d_adjT(const double *X, const double *a, double *b, int64_t B, void *stream);
+int se3d_act(const double *X, const double *p, double *q, int64_t B, void *stream);
+int se3d_act4(const double *X, const double *p, double *q, int64_t B, void *stream);
+int se3d_as_matrix(const double *X, double *T, int64_t B, void *stream);
 
 /* ---- misc ----------------------------------------------------------------------------------- */
 const char *ba_error_string(int code);

@@ -13,6 +13,12 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
+def _golden_large(name):
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+    return np.load(path)
+
+
 def _oracle():
     from oracle import ba_oracle
     return ba_oracle
@@ -30,7 +36,7 @@ def test_ba_sequence_matches_reference_fp64(name):
     print(f"\n{name}: ours vs fp64 poses {ep:.2e} disps {ed:.2e} | reference fp32 vs fp64 poses {rp:.2e} disps {rd:.2e}")
     assert np.isfinite(P).all() and np.isfinite(D).all()
     assert ep < TOL, f"poses {ep}"
-    assert ed < max(TOL, 2 * rd), f"disps {ed} (reference fp32 itself: {rd})"
+    assert ed < TOL, f"disps {ed} (reference fp32 itself: {rd})"
 
 
 @pytest.mark.parametrize("name", ["cfg1_rgbd", "slam_dual", "random_rgbd", "random2_ba", "tiny_bounds"])
@@ -165,6 +171,80 @@ def test_cholesky_failure_and_nan_are_silent():
     assert torch.isfinite(p).all() and not torch.equal(p, t["patches"])
 
 
+def test_nan_retry_branch_matches_reference_semantics():
+    """ba.py:324-325 (rgbd variant): NaN in dX -> one more solve with lm = 1e-3. A NaN target on an edge is rejected by
+    the masks (ba.py:233-242) but, exactly as in the reference, the mask multiplies (0 * NaN = NaN): the reduced
+    right-hand side turns NaN while S stays finite, the factorisation succeeds, dX is NaN, the retry is taken (status
+    bit 1) and — S being the same — ends NaN as well. Outputs must carry NaN exactly where the oracle's do and agree
+    elsewhere. (A retry that *repairs* dX needs an overflow inside the fp32 LAPACK solve; the fp64 band solver has no such
+    case, so the branch is pinned on what both sides can reach.) BA (no retry in the reference, ba.py:205-207) must not
+    set the bit."""
+    from batrack_b200 import synth
+    from batrack_b200.ba import BA, BA_rgbd_droid
+    from batrack_b200.lietorch import SE3
+    from batrack_b200.plan import get_plan
+    from gpu_util import as_cuda
+    prob = synth.make_config("cfg1")
+    prob.targets = prob.targets.copy()
+    prob.targets[37] = np.nan
+    t = as_cuda(prob)
+    w = torch.ones(1, prob.E, 2, device="cuda")
+    plan = get_plan(t["ii"], t["jj"], t["kk"], t["poses"].shape[1], t["patches"].shape[1])
+    G, p = BA_rgbd_droid(SE3(t["poses"]), t["patches"], t["patches_monodisp"], t["intrinsics"], t["targets_2d"], None, w,
+                         prob.lmbda, t["ii"], t["jj"], t["kk"], prob.bounds, ep=prob.ep, fixedp=prob.fixedp, loss=prob.loss,
+                         alpha=prob.alpha)
+    st = plan.status()
+    assert st & 2 and not st & 1, st                                       # retry taken, factorisation itself fine
+    P64, D64 = _oracle().run_sequence(prob, [prob.weights], [False], torch.float64)
+    Pg, Dg = G.data[0].cpu().numpy(), p[0, :, 2, 0, 0].cpu().numpy()
+    assert np.array_equal(np.isnan(Pg), np.isnan(P64[0])) and np.isnan(Pg).any()
+    assert np.array_equal(np.isnan(Dg), np.isnan(D64[0]))
+    fp, fd = ~np.isnan(P64[0]), ~np.isnan(D64[0])
+    assert fp.any() and rel_err(Pg[fp], P64[0][fp]) < TOL                  # the fixed pose stays finite
+    assert not fd.any() or rel_err(Dg[fd], D64[0][fd]) < TOL
+    BA(SE3(t["poses"]), t["patches"], t["intrinsics"], t["targets_2d"], w, prob.lmbda, t["ii"], t["jj"], t["kk"],
+       prob.bounds, ep=prob.ep, fixedp=prob.fixedp, loss=prob.loss)
+    assert not plan.status() & 2
+
+
+def test_streaming_give_up_path_is_correct():
+    """The band solver starts next to the Schur kernel and waits for its completion flags with a bounded spin. When the
+    producer does not get there in time (kernels serialised by a profiler, a busy GPU) it gives up, reports status bit 3
+    and a stand-by launch redoes the solve on the finished system. Forced here on the headline graph with a spin bound of
+    a few microseconds (BA_OPT_SPIN_CAP) and a Schur kernel throttled to one CTA per SM (BA_OPT_STREAM_SMEM_KB); the
+    result must still match the fp64 oracle."""
+    from batrack_b200 import synth
+    from batrack_b200.ba import BA_rgbd_droid
+    from batrack_b200.lietorch import SE3
+    from batrack_b200.plan import Plan
+    from gpu_util import as_cuda
+    prob = synth.make_config("cfg3")
+    t = as_cuda(prob)
+    plan = Plan(t["ii"], t["jj"], t["kk"], t["poses"].shape[1], t["patches"].shape[1])
+    w = torch.from_numpy(prob.weights).cuda()[None]
+
+    def call():
+        return BA_rgbd_droid(SE3(t["poses"]), t["patches"], t["patches_monodisp"], t["intrinsics"], t["targets_2d"], None,
+                             w, prob.lmbda, t["ii"], t["jj"], t["kk"], prob.bounds, ep=prob.ep, fixedp=prob.fixedp,
+                             loss=prob.loss, alpha=prob.alpha, plan=plan)
+
+    G0, p0 = call()
+    assert plan.status() == 0
+    plan.set_option("spin_cap", 1)
+    plan.set_option("stream_smem_kb", 200)
+    assert plan.get_option("spin_cap") == 1 and plan.get_option("stream") == 1
+    G1, p1 = call()
+    assert plan.status() & 8, "the streamed solve was expected to give up"
+    assert rel_err(G1.data.cpu().numpy(), G0.data.cpu().numpy()) < 1e-6 and rel_err(p1.cpu().numpy(), p0.cpu().numpy()) < 1e-6
+    z = _golden_large("cfg3_x10_sparse64.npz")
+    assert rel_err(G1.data[0].cpu().numpy(), z["poses"][0]) < TOL
+    assert rel_err(p1[0, :, 2, 0, 0].cpu().numpy(), z["disps"][0].astype(np.float64)) < TOL
+    plan.set_option("spin_cap", 0)
+    plan.set_option("stream_smem_kb", 0)
+    call()
+    assert plan.status() == 0
+
+
 def test_se3_ops_match_reference():
     from batrack_b200.lietorch import SE3
     z = Fixture("se3_ops")
@@ -214,24 +294,27 @@ def test_mid_graph_against_sparse_oracle():
     assert ep < TOL and ed < TOL
 
 
-def test_headline_graph_properties():
-    """cfg3 (256 KF / 65 536 tracks / 1 245 184 edges) at full size: size-independent properties —
-    finite outputs, the reprojection error of the huber-inlier set falls monotonically over LM
-    iterations and approaches the 0.5 px target noise, the first pose stays fixed, and the first
-    iteration matches the sparse fp64 oracle."""
+def test_headline_graph_all_ten_iterations():
+    """cfg3 (256 KF / 65 536 tracks / 1 245 184 edges, BASELINE.json configs[2]: 10 LM iterations): EVERY one of the 10
+    chained iterations against the sparse fp64 oracle's results (tests/golden/cfg3_x10_sparse64.npz, produced by
+    tests/golden/make_golden_large.py), plus the size-independent properties."""
     from batrack_b200 import synth
     from gpu_util import run_ours
     prob = synth.make_config("cfg3")
-    P, D = run_ours(prob, [prob.weights] * 6, [False] * 6)
+    z = _golden_large("cfg3_x10_sparse64.npz")
+    assert int(z["edges"]) == prob.E and int(z["iters"]) == 10
+    P, D = run_ours(prob, [prob.weights] * 10, [False] * 10)
     assert np.isfinite(P).all() and np.isfinite(D).all()
     assert rel_err(P[:, 0], np.broadcast_to(prob.poses[0], P[:, 0].shape)) < 1e-6
-    errs_p = [np.abs(P[k] - prob.gt_poses).max() for k in range(6)]
+    errs_p = [np.abs(P[k] - prob.gt_poses).max() for k in range(10)]
     print("\ncfg3 pose error vs GT per iteration:", ["%.2e" % e for e in errs_p])
     assert errs_p[-1] < errs_p[0]
-    P64, D64 = _oracle().run_sequence(prob, [prob.weights], [False], torch.float64, mode="sparse")
-    ep, ed = rel_err(P[0], P64[0]), rel_err(D[0], D64[0])
-    print(f"cfg3 iteration 1 vs fp64 sparse oracle: poses {ep:.2e} disps {ed:.2e}")
-    assert ep < TOL and ed < TOL
+    worst = (0.0, 0.0)
+    for k in range(10):
+        ep, ed = rel_err(P[k], z["poses"][k]), rel_err(D[k], z["disps"][k].astype(np.float64))
+        worst = (max(worst[0], ep), max(worst[1], ed))
+        assert ep < TOL and ed < TOL, f"iteration {k + 1}: poses {ep} disps {ed}"
+    print(f"cfg3 iterations 1..10 vs fp64 sparse oracle: worst poses {worst[0]:.2e} disps {worst[1]:.2e}")
 
 
 def test_davis_like_window_against_dense_oracle():
@@ -249,30 +332,41 @@ def test_davis_like_window_against_dense_oracle():
     assert ep < TOL and ed < TOL
 
 
-def test_1024_keyframe_graph_properties():
-    """cfg5 (1024 KF / 262 144 tracks / 4 980 736 edges) on one device: banded reduced system with 6138
-    unknowns. Size-independent properties + the first pose update against the sparse fp64 oracle restricted to
-    what is cheap on the host: the reduced system's solution satisfies (S + damping) dX = y."""
+def test_1024_keyframe_graph_against_sparse_oracle():
+    """cfg5 (1024 KF / 262 144 tracks / 4 980 736 edges, BASELINE.json configs[4]) on one device: banded reduced system
+    with 6138 unknowns; poses and disparities of two chained iterations against the sparse fp64 oracle
+    (tests/golden/cfg5_x2_sparse64.npz, produced by tests/golden/make_golden_large.py — the dense reference cannot hold
+    this graph: 6.4 GB per E-sized temporary)."""
     from batrack_b200 import synth
     from gpu_util import run_ours
     prob = synth.make_config("cfg5")
+    z = _golden_large("cfg5_x2_sparse64.npz")
+    assert int(z["edges"]) == prob.E
     P, D, plan, t = run_ours(prob, [prob.weights] * 2, [False] * 2, return_plan=True)
     assert np.isfinite(P).all() and np.isfinite(D).all()
     assert plan.info.banded == 1 and plan.info.n_total == 1024 and plan.info.block_bandwidth == 18
     assert plan.status() == 0
-    assert rel_err(P[:, 0], np.broadcast_to(prob.poses[0], P[:, 0].shape)) < 1e-6
-    e0 = np.abs(prob.poses.astype(np.float64) - prob.gt_poses).max()
-    e2 = np.abs(P[1] - prob.gt_poses).max()
-    print(f"\ncfg5 pose error vs GT: start {e0:.2e} -> after 2 iterations {e2:.2e}")
-    assert e2 < e0
-    # residual of the damped reduced system of the LAST call, checked on the host in fp64 from the debug view
-    n = 1023
-    dbg = plan.debug(n)
-    S, y, dX = (dbg[k].double().cpu() for k in ("S", "y", "dX"))
-    A = S + torch.diag(prob.ep + 1e-4 * torch.diagonal(S))
-    res = (A @ dX - y).abs().max() / y.abs().max()
-    print(f"cfg5 reduced-system residual |A dX - y| / |y| = {res:.2e}")
-    assert res < 1e-5          # S, y are read back through an fp32 debug view
+    for k in range(2):
+        ep, ed = rel_err(P[k], z["poses"][k]), rel_err(D[k], z["disps"][k].astype(np.float64))
+        print(f"\ncfg5 iteration {k + 1} vs fp64 sparse oracle: poses {ep:.2e} disps {ed:.2e}")
+        assert ep < TOL and ed < TOL
+
+
+def test_sintel_like_full_sequence_window():
+    """cfg4 stand-in (configs/sintel.yaml: 256 patches / frame, S_slam 12, kf_stride 2; "full-sequence" = the removal and
+    optimisation windows cover all 50 frames, so 48 free poses and every keyframe step's 18 432 edges stay in the
+    graph): the reference's own bookkeeping replayed on synthetic tracks, update() pairing x 2, against the fp64 oracle."""
+    from batrack_b200 import synth
+    from gpu_util import run_ours
+    ps, w_all = synth.make_slam_problem(n_frames=50, patches_per_frame=256, seed=4, buffer_size=64, opt_window=64,
+                                        removal_window=64, width=1024, height=436, name="sintel_like")
+    assert ps.fixedp == 1 and ps.E > 350000
+    ws, so = [ps.weights, w_all] * 2, [False, True] * 2
+    P, D = run_ours(ps, ws, so)
+    P64, D64 = _oracle().run_sequence(ps, ws, so, torch.float64, mode="sparse")
+    ep, ed = rel_err(P, P64), rel_err(D, D64)
+    print(f"\nsintel-like ({ps.E} edges, 48 free poses): poses {ep:.2e} disps {ed:.2e}")
+    assert ep < TOL and ed < TOL
 
 
 def test_structure_only_and_ba_variant_on_mid_graph():

@@ -62,7 +62,15 @@ for sv in solvers:
             twist = nt >= plan.get_option("twist_min")
             ncol = (nt - 16) // 2 if twist else nt
             h = tr[:16 * 4096].reshape(4096, 16)
-            if ncol > 4:
+            if ncol > 4 and sv == "diag":
+                a, nx = h[1:ncol - 1], h[2:ncol]
+                m = lambda x: float(x.mean())
+                step = (h[ncol - 1, 0] - h[1, 0]) / (ncol - 2)
+                print(f"   trace: tiles {nt} twist {int(twist)} | tile warp 0: fetch+wait panels {m(a[:, 1] - a[:, 0]):.0f} first tiles+ship {m(a[:, 2] - a[:, 1]):.0f} "
+                      f"rest of U {m(a[:, 3] - a[:, 2]):.0f} loop {m(nx[:, 0] - a[:, 3]):.0f} | panel warp 0: wait A {m(a[:, 5] - a[:, 4]):.0f} wait W {m(a[:, 6] - a[:, 5]):.0f} "
+                      f"tiles {m(a[:, 7] - a[:, 6]):.0f} deferred {m(nx[:, 4] - a[:, 7]):.0f} | factor warp: wait D {m(a[:, 9] - a[:, 8]):.0f} A {m(a[:, 10] - a[:, 9]):.0f} "
+                      f"loop {m(nx[:, 8] - a[:, 10]):.0f} | step {step:.0f} cycles")
+            elif ncol > 4:
                 a, nx = h[1:ncol - 1], h[2:ncol]
                 d = [(a[:, 1] - a[:, 0]).mean(), (a[:, 2] - a[:, 1]).mean(), (a[:, 3] - a[:, 2]).mean(),
                      (a[:, 4] - a[:, 3]).mean(), (a[:, 5] - a[:, 4]).mean(), (nx[:, 0] - a[:, 5]).mean(),
