@@ -792,7 +792,8 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
     break;
   }
   if (feed.mode == 1 && tau == 0 && s_giveup) atomicOr(feed.redo, 1);
-  if (tau == 0 && side == 0) cv.status[0] = status | ((feed.mode == 1 && s_giveup) ? 8 : 0);
+  // bit 3: the streamed solve gave up waiting (mode 1) / this stand-by launch redid it (mode 2 only gets here then)
+  if (tau == 0 && side == 0) cv.status[0] = status | (((feed.mode == 1 && s_giveup) || feed.mode == 2) ? 8 : 0);
   if (phase && tau == 0) phase[3] = clock64();
 }
 
