@@ -113,6 +113,8 @@ struct BaPlan {
   long long *trace_buf;
   ba::PlanView v;
   int n_total_layout, bwb_layout;      // what the reduced-system layout uses (>= the local values)
+  int min_unit, max_unit;              // shortest / longest Schur unit (tracks): which of the two Schur kernels have work
+  int min_ounit, max_ounit;            // the same for the units of the streaming hand-over
   int device;
   // workspace
   double *SY, *L, *dX, *Wg;            // Wg: inverted diagonal tiles of the tensor-core solver
@@ -172,9 +174,9 @@ int solve_diag_prepare_device();
 int solve_mma_prepare_device(int dev, cudaStream_t s);
 int kernels_prepare_device();
 int schur_tc_prepare_device();
-constexpr int kSchurTcMaxFree = 21;     // free pose slots of a group the tensor-core Schur kernel covers (6 * 21 + 1 <= 128 rows)
+constexpr int kSchurTcMaxFree = 20;     // free pose slots of a group the tensor-core Schur kernel covers (6 * 20 + 1 <= 128 operand rows)
 int launch_schur_tc(const PlanView &pv, const CallView &cv, int n_units, const int *ut0, const int *ugrp, const int *order,
-                    int *flags, int epoch, int acc_chunks, int min_tracks, cudaStream_t s);
+                    int *flags, int epoch, int acc_chunks, int min_tracks, long long *trace, cudaStream_t s);
 constexpr int kSchurTcMinTracks = 96;   // shorter units stay on the SIMT kernel (faster there, and the 8-keyframe class of
                                         // ill-conditioned small windows keeps plain fp32 products)
 }  // namespace ba
@@ -185,7 +187,7 @@ inline SolveFeed make_feed(const BaPlan *pl, const int *flags, const int *top_ne
   SolveFeed f;
   f.flags = flags; f.top_need = top_need; f.bot_need = bot_need; f.epoch = epoch; f.n_units = n_units; f.fixedp = fixedp;
   f.mode = mode; f.redo = redo; f.shape_key = const_cast<long long *>(&pl->solve_shape_key);
-  f.spin_cap = pl->opt.spin_cap; f.twist_min = pl->opt.twist_min; f.trace = pl->opt.trace ? pl->trace_buf : nullptr;
+  f.spin_cap = pl->opt.spin_cap; f.twist_min = pl->opt.twist_min; f.trace = (pl->opt.trace & 1) ? pl->trace_buf : nullptr;
   return f;
 }
 }  // namespace ba

@@ -11,7 +11,11 @@ namespace ba {
 
 // Reduced-system accumulators are fp64: the per-edge math is fp32 like the reference's, but every sum
 // that feeds the (ill-conditioned) reduced solve is carried in double — see DESIGN.md §Precision.
-__device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
+// fire-and-forget reduction (REDG): atomicAdd with an unused result sometimes compiles to ATOMG, whose response
+// travels back through the crossbar and keeps the warp from retiring
+__device__ __forceinline__ void red_add(double *addr, double v) {
+  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
 
 // Ad(X)^T applied in double (R, t are the fp32 pair constants)
 __device__ __forceinline__ void adjT_apply_d(const float *R, Vec3 t, const double *a, double *b) {
@@ -1382,8 +1386,10 @@ static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int str
     if (smem > 200 * 1024) return BA_ERR_ARG;
     // tensor-core kernel (tcgen05, 3xTF32) for every unit whose free pose slots fit 128 operand rows; the SIMT kernel
     // takes the rest (and everything with BA_OPT_SCHUR = 1)
-    const bool tc = pl->opt.schur == 0;
-    const bool simt = true;                // it also takes the units shorter than kSchurTcMinTracks (exits at once elsewhere)
+    // (it exits at once on the units of the other kernel). Either launch is skipped when the plan knows it has no work.
+    const int umin = streaming ? pl->min_ounit : pl->min_unit, umax = streaming ? pl->max_ounit : pl->max_unit;
+    const bool tc = pl->opt.schur == 0 && umax >= kSchurTcMinTracks;
+    const bool simt = !tc || umin < kSchurTcMinTracks || pl->info.max_slots > kSchurTcMaxFree;
     if (streaming) {
       int *flags = reinterpret_cast<int *>(cv.y + cv.M);
       const SolveFeed feed = make_feed(pl, flags, pv.top_need, pv.bot_need, 1, pv.n_ounits, pb->fixedp, 1, pl->status + 2);
@@ -1392,13 +1398,13 @@ static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int str
       if (rc) return rc;
       BA_CUDA(cudaEventRecord(pl->ev_solved, pl->solve_stream));
       const size_t stream_smem = (size_t)pl->opt.stream_smem_kb * 1024;   // BA_OPT_STREAM_SMEM_KB: throttle occupancy (tests force the give-up path with it)
-      if (tc) { rc = launch_schur_tc(pv, cv, pv.n_ounits, pv.o_t0, pv.o_grp, pv.o_order, flags, 1, pl->opt.schur_acc, kSchurTcMinTracks, s); if (rc) return rc; }
+      if (tc) { rc = launch_schur_tc(pv, cv, pv.n_ounits, pv.o_t0, pv.o_grp, pv.o_order, flags, 1, pl->opt.schur_acc, kSchurTcMinTracks, (pl->opt.trace & 2) ? pl->trace_buf : nullptr, s); if (rc) return rc; }
       if (simt) {
         k_schur<<<pv.n_ounits, kSchurThreads, std::max(smem, stream_smem), s>>>(pv, cv, tile, pv.o_t0, pv.o_grp, pv.o_order, flags, 1, tc ? kSchurTcMinTracks : 0);
         BA_LAUNCH_CHECK();
       }
     } else {
-      if (tc) { rc = launch_schur_tc(pv, cv, pv.n_units, pv.u_t0, pv.u_grp, nullptr, nullptr, 0, pl->opt.schur_acc, kSchurTcMinTracks, s); if (rc) return rc; }
+      if (tc) { rc = launch_schur_tc(pv, cv, pv.n_units, pv.u_t0, pv.u_grp, nullptr, nullptr, 0, pl->opt.schur_acc, kSchurTcMinTracks, (pl->opt.trace & 2) ? pl->trace_buf : nullptr, s); if (rc) return rc; }
       if (simt) { k_schur<<<pv.n_units, kSchurThreads, smem, s>>>(pv, cv, tile, pv.u_t0, pv.u_grp, nullptr, nullptr, 0, tc ? kSchurTcMinTracks : 0); BA_LAUNCH_CHECK(); }
     }
   }

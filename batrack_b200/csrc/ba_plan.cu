@@ -38,7 +38,7 @@ int set_cuda_error(cudaError_t e, const char *what) {
 }
 
 // meta block written by the prep kernels
-enum { META_ERR = 0, META_MAXPOSE, META_NOTIDENT, META_DMAX, META_WMAX, META_SPAN, META_NIRREG, META_DMAX_IRREG, META_COUNT = 8 };
+enum { META_ERR = 0, META_MAXPOSE, META_NOTIDENT, META_DMAX, META_WMAX, META_SPAN, META_NIRREG, META_DMAX_IRREG, META_MINUNIT, META_MINOUNIT, META_COUNT = 10 };
 
 __global__ void k_prep_keys(const int64_t *__restrict__ ii, const int64_t *__restrict__ jj,
                             const int64_t *__restrict__ kk, int64_t E, int N, int NM,
@@ -112,7 +112,7 @@ __global__ void k_fill_groups(const int *__restrict__ gflag, const int *__restri
 // Groups g_lo <= g < g_hi use units of at most tc_mid tracks instead (streaming Schur units: small at both ends of
 // the pose range, where the solver starts, large in the middle).
 __global__ void k_chunk_flags(const int *__restrict__ t_grp, const int *__restrict__ g_t0, int m, int tc,
-                              int *__restrict__ cflag, int g_lo = 0, int g_hi = 0, int tc_mid = 0) {
+                              int *__restrict__ cflag, int *__restrict__ min_len = nullptr, int g_lo = 0, int g_hi = 0, int tc_mid = 0) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m) return;
   const int g = t_grp[t];
@@ -120,7 +120,9 @@ __global__ void k_chunk_flags(const int *__restrict__ t_grp, const int *__restri
   const int T = g_t0[g + 1] - g_t0[g];
   const int pieces = (T + tc - 1) / tc;
   const int len = ((T + pieces - 1) / pieces + 3) & ~3;          // multiple of 4: 16-byte aligned starts in the E rows
-  cflag[t] = ((t - g_t0[g]) % len == 0) ? 1 : 0;
+  const int rel = t - g_t0[g];
+  cflag[t] = (rel % len == 0) ? 1 : 0;
+  if (min_len && rel % len == 0) atomicMin(min_len, min(len, T - rel));     // shortest unit (the last piece of a group)
 }
 __global__ void k_fill_chunks(const int *__restrict__ cflag, const int *__restrict__ cinc,
                               const int *__restrict__ t_grp, int m, int *__restrict__ c_t0,
@@ -358,14 +360,14 @@ static void options_from_env(BaOptions *o) {
     else if (e[0] == 'w' || e[0] == '2') o->solver = 2;
     else if ((e[0] == 'd' && e[1] == 'e') || e[0] == '3') o->solver = 3;
   }
-  o->stream = env_int("BA_STREAM", 1) ? 1 : 0;
+  o->stream = env_int("BA_STREAM", 0) ? 1 : 0;   // off: with the tensor-core Schur kernel the plain sequence is faster
   o->stream_smem_kb = std::max(0, env_int("BA_STREAM_SMEM_KB", 0));
   o->schur_tile = std::max(4, env_int("BA_SCHUR_TILE", 64));
   o->twist_min = std::max(17, env_int("BA_TWIST_MIN", 64));
   o->spin_cap = std::max(0, env_int("BA_SPIN_CAP", 0));
   o->trace = env_int("BA_SOLVER_TRACE", 0) ? 1 : 0;
   o->schur = env_int("BA_SCHUR", 0) ? 1 : 0;
-  o->schur_acc = std::min(8, std::max(1, env_int("BA_SCHUR_ACC", 2)));
+  o->schur_acc = std::min(8, std::max(1, env_int("BA_SCHUR_ACC", 4)));
 }
 template <typename T> static cudaError_t own(BaPlan *pl, T **p, size_t n) {
   void *q = nullptr;
@@ -484,6 +486,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     int *eperm;
     PL_CUDA(own(pl, &eperm, E));
     PL_CUDA(cudaMemsetAsync(meta, 0, META_COUNT * sizeof(int), s));
+    PL_CUDA(cudaMemsetAsync(meta + META_MINUNIT, 0x7f, 2 * sizeof(int), s));
 
     k_prep_keys<<<cdiv(E, TB), TB, 0, s>>>(ii, jj, kk, E, N, NM, key, val, eij, meta); PL_LAUNCH();
     {
@@ -549,13 +552,15 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     int to = 64;                                       // Schur units of the streaming hand-over to the solver
     if (const char *e = getenv("BA_STREAM_TU")) to = std::max(16, atoi(e) & ~3);
     const int unit_len[4] = {tc, tu, tx, to};
+    int to_max = to;
     for (int pass = 0; pass < 4; ++pass) {
       if (pass == 3) {                                 // optionally large units in the middle of the pose range (measured at
         int gend = 1 << 30;                            // 256 KF: 24 / 40 / 64 end groups small: 525 / 517 / 492 us, all small 494)
         if (const char *e = getenv("BA_STREAM_GEND")) gend = std::max(0, atoi(e));
-        k_chunk_flags<<<cdiv(m, TB), TB, 0, s>>>(t_grp, g_t0, m, unit_len[pass], cflag, std::min(gend, G), G - std::min(gend, G), 256);
+        if (gend < G - gend) to_max = std::max(to, 256);
+        k_chunk_flags<<<cdiv(m, TB), TB, 0, s>>>(t_grp, g_t0, m, unit_len[pass], cflag, meta + META_MINOUNIT, std::min(gend, G), G - std::min(gend, G), 256);
       } else {
-        k_chunk_flags<<<cdiv(m, TB), TB, 0, s>>>(t_grp, g_t0, m, unit_len[pass], cflag);
+        k_chunk_flags<<<cdiv(m, TB), TB, 0, s>>>(t_grp, g_t0, m, unit_len[pass], cflag, pass == 1 ? meta + META_MINUNIT : nullptr);
       }
       PL_LAUNCH();
       PL_CUDA(inclusive_sum(sc, cflag, cinc, m, s));
@@ -633,6 +638,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
     in.max_slots = hmeta[META_WMAX]; in.block_bandwidth = hmeta[META_SPAN]; in.perm_identity = v.perm_identity;
     pl->n_total_layout = in.n_total;
     pl->bwb_layout = in.block_bandwidth;
+    pl->min_unit = hmeta[META_MINUNIT]; pl->min_ounit = hmeta[META_MINOUNIT]; pl->max_unit = tu; pl->max_ounit = to_max;
 
     PL_CUDA(own(pl, &pl->Est, (size_t)esize + 8));
     PL_CUDA(cudaMemsetAsync(pl->Est, 0, ((size_t)esize + 8) * sizeof(float), s));   // row padding stays zero (finite) for ever
@@ -685,7 +691,7 @@ extern "C" int ba_plan_set_option(BaPlan *pl, int32_t key, int32_t value) {
         BA_CUDA(cudaMalloc(&pl->trace_buf, kTraceValues * sizeof(long long)));
         BA_CUDA(cudaMemset(pl->trace_buf, 0, kTraceValues * sizeof(long long)));
       }
-      pl->opt.trace = value ? 1 : 0;
+      pl->opt.trace = value;              // bit 0: band solver, bit 1: tensor-core Schur kernel
       break;
     case BA_OPT_SCHUR: if (value < 0 || value > 1) return BA_ERR_ARG; pl->opt.schur = value; break;
     case BA_OPT_SCHUR_ACC: if (value < 1 || value > 8) return BA_ERR_ARG; pl->opt.schur_acc = value; break;

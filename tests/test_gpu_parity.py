@@ -228,6 +228,7 @@ def test_streaming_give_up_path_is_correct():
                              w, prob.lmbda, t["ii"], t["jj"], t["kk"], prob.bounds, ep=prob.ep, fixedp=prob.fixedp,
                              loss=prob.loss, alpha=prob.alpha, plan=plan)
 
+    plan.set_option("stream", 1)
     G0, p0 = call()
     assert plan.status() == 0
     plan.set_option("spin_cap", 1)
@@ -473,10 +474,11 @@ def test_host_buffer_pipeline_equals_device_call():
                    ps.lmbda, ps.bounds, *outs[0])
 
 
+@pytest.mark.parametrize("stream", [0, 1])
 @pytest.mark.parametrize("n_kf", [64, 112])
-def test_band_solver_failure_is_silent_and_recoverable(n_kf):
+def test_band_solver_failure_is_silent_and_recoverable(n_kf, stream):
     """The band (DMMA) solver — plain at 64 keyframes, twisted over two CTAs at 112 (>= 64 tile columns) — launched
-    next to the Schur kernel (streaming hand-over): a failed factorisation (ba.py:9-13) leaves the poses unchanged
+    behind the Schur kernel (default) or next to it (streaming hand-over, option "stream"): a failed factorisation (ba.py:9-13) leaves the poses unchanged
     while the depths still move, and the next call on the same plan is correct again (flags carry a new epoch)."""
     from batrack_b200 import synth
     from batrack_b200.ba import BA_rgbd_droid
@@ -488,6 +490,7 @@ def test_band_solver_failure_is_silent_and_recoverable(n_kf):
     N, NM = t["poses"].shape[1], t["patches"].shape[1]
     plan = Plan(t["ii"], t["jj"], t["kk"], N, NM)
     assert plan.info.banded
+    plan.set_option("stream", stream)
     w = torch.from_numpy(prob.weights).cuda()[None]
 
     def call(ep):
@@ -508,9 +511,11 @@ def test_band_solver_failure_is_silent_and_recoverable(n_kf):
     assert rel_err(G0.data[0].cpu().numpy(), P64[0]) < TOL and rel_err(p0[0, :, 2, 0, 0].cpu().numpy(), D64[0]) < TOL
 
 
-def test_ba_step_replays_from_a_cuda_graph():
-    """the step must be graph-capturable. A captured BA_rgbd_droid call (band solver streamed next to the
-    Schur kernel: cross-stream events, no host-side per-call state) is replayed on new weights and matches eager calls."""
+@pytest.mark.parametrize("stream", [0, 1])
+def test_ba_step_replays_from_a_cuda_graph(stream):
+    """the step must be graph-capturable. A captured BA_rgbd_droid call (plain, and with the band solver
+    streamed next to the Schur kernel: cross-stream events, no host-side per-call state) is replayed on new weights and
+    matches eager calls."""
     from batrack_b200 import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.lietorch import SE3
@@ -520,6 +525,7 @@ def test_ba_step_replays_from_a_cuda_graph():
     t = as_cuda(prob)
     N, NM = t["poses"].shape[1], t["patches"].shape[1]
     plan = Plan(t["ii"], t["jj"], t["kk"], N, NM)
+    plan.set_option("stream", stream)
     w = torch.from_numpy(prob.weights).cuda()[None].clone()
 
     def call():

@@ -29,7 +29,7 @@ def call(plan):
 
 
 ref = None
-combos = [(1, 0, 64, 2), (1, 1, 64, 2), (0, 0, 64, 1), (0, 0, 64, 2), (0, 0, 64, 4), (0, 0, 64, 8), (0, 1, 64, 2), (0, 1, 128, 2), (0, 1, 256, 2), (1, 1, 256, 2)]
+combos = [(1, 0, 64, 4), (0, 0, 64, 4)]
 for schur, stream, tu, acc_chunks in combos:
     if True:
         os.environ["BA_STREAM_TU"] = str(tu)
