@@ -269,7 +269,11 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
 #pragma unroll
           for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j <= i; ++j) a[tri8(i, j)] = Dsm[i * kPs + j];
+            for (int j = 0; j <= i; j += 2) {                      // 16-byte broadcast loads (rows are 96 bytes apart)
+              const double2 v = *reinterpret_cast<const double2 *>(Dsm + i * kPs + j);
+              a[tri8(i, j)] = v.x;
+              if (j + 1 <= i) a[tri8(i, j + 1)] = v.y;
+            }
           double zr[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) zr[k] = z[8 * J + k];
@@ -280,6 +284,8 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
           // nobody reads: `ok` turns into the failure flag (potrf info != 0, ba.py:11).
           bool ok = true;
           double wv[8];
+          double *wdst = lane < 8 ? Wsm + 64 * p + (lane & 3) * 2 + (lane >> 2) : zJ + 8 * p;
+          const int wstep = lane < 8 ? 8 : 1;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const double piv = a[tri8(k, k)];
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
             double y;                                              // seed from the high word (~2^-20) + one Newton step
             asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(piv));
             const double inv = fma(fma(-piv * y, 0.5 * y, 0.5), y, y);
-            double sv = lane == 8 ? zr[k] : (lane == k ? 1.0 : 0.0);
+            double sv = lane == 8 ? zr[k] : (lane == k ? -1.0 : 0.0);   // lanes 0-7 solve for the columns of -W
 #pragma unroll
             for (int j = 0; j < k; ++j) sv -= a[tri8(k, j)] * wv[j];
             wv[k] = sv * inv;
@@ -298,21 +304,20 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
 #pragma unroll
               for (int i = j; i < 8; ++i) a[tri8(i, j)] -= a[tri8(i, k)] * a[tri8(j, k)];
           }
-          if (ok) {
-            if (lane < 8) {
+          // lanes 0-7: column `lane` of -W (operand layout); lane 8: zJ. One predicated store per row, no divergence; a
+          // failed column publishes garbage nobody reads (the flag goes with it)
+          if (lane <= 8) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) Wsm[64 * p + op_idx(i, lane)] = -wv[i];
-            } else if (lane == 8) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { z[8 * J + i] = wv[i]; zJ[8 * p + i] = wv[i]; }
-            }
-          } else if (lane == 0) {
-            s_fail = 1;
+            for (int i = 0; i < 8; ++i) wdst[i * wstep] = wv[i];
           }
-          if (lane == 0) s_colfail[p] = ok ? 0 : 1;
+          if (lane == 0) { s_colfail[p] = ok ? 0 : 1; if (!ok) s_fail = 1; }
           __syncwarp();
           BA_TR(10);
           bar_arrive(kBarW + p, kCntW);                            // W_J, zJ (or the failure flag) published
+          if (ok && lane == 8) {                                   // the forward solution of the block (the back substitution reads it)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[8 * J + i] = wv[i];
+          }
           bar_sync(kBarA + p, kCntA);                              // -A_{J+1,J} is in Asm[p] (shipped a column ago)
           if (!ok) { stop = true; break; }
           if (J + 1 < je || handover) {
