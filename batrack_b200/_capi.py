@@ -11,7 +11,7 @@ LOSS_IDS = {"trivial": 0, "huber": 1, "cauchy": 2}      # compute_kernel_weight,
 # BA_OPT_* keys of include/batrack_ba.h
 OPTIONS = {"solver": 1, "stream": 2, "stream_smem_kb": 3, "schur_tile": 4, "twist_min": 5, "spin_cap": 6,
            "solver_trace": 7, "schur": 8, "schur_acc": 9}
-SOLVERS = {"diag": 0, "mma": 1, "window": 2, "dense": 3}
+SOLVERS = {"auto": 0, "mma": 1, "window": 2, "dense": 3, "tiles": 4, "diag": 5}
 
 
 class BaPlanInfo(C.Structure):

@@ -96,7 +96,8 @@ struct CallView {
 
 // Per-plan switches (ba_plan_set_option); defaults come from the environment once, at plan creation.
 struct BaOptions {
-  int solver;          // BA_OPT_SOLVER: 0 diagonal-ownership DMMA band solver, 1 legacy circular-ownership DMMA solver, 2 scalar window, 3 dense
+  int solver;          // BA_OPT_SOLVER: 0 automatic (tile solver for short systems, diagonal-ownership DMMA band solver for long bands), 1 legacy
+                       // circular-ownership DMMA solver, 2 scalar window, 3 dense, 4 shared-memory tile solver, 5 diagonal-ownership band solver
   int stream;          // BA_OPT_STREAM: Schur -> solve streaming hand-over in ba_step
   int stream_smem_kb;  // BA_OPT_STREAM_SMEM_KB: dynamic shared memory forced on the streamed Schur kernel (occupancy throttle, tests)
   int schur_tile;      // BA_OPT_SCHUR_TILE: tracks per cp.async stage of the SIMT Schur kernel
@@ -169,6 +170,11 @@ int launch_solve_band_mma(const CallView &cv, int allow_retry, double *scratch, 
 // diagonal-ownership band solver (ba_solve_diag.cu): same contract, the default
 int launch_solve_band_diag(const CallView &cv, int allow_retry, double *scratch, const SolveFeed &feed, cudaStream_t s);
 size_t solve_diag_smem_bytes(int M);
+// shared-memory tile solver for small / medium systems (ba_solve_tile.cu): one CTA, band window as 8x8 tiles
+bool solve_tiles_applies(int M, int bw, int *nbt_out);
+size_t solve_tiles_scratch_doubles(int M, int bw);
+int launch_solve_tiles(const CallView &cv, int allow_retry, double *scratch, long long *trace, cudaStream_t s);
+int solve_tiles_prepare_device();
 // per-device one-time setup (function attributes, static tables); called from ba_plan_create under a lock
 int solve_diag_prepare_device();
 int solve_mma_prepare_device(int dev, cudaStream_t s);

@@ -1311,9 +1311,23 @@ static int make_call(BaPlan *pl, const BaProblem *pb, CallView *cv) {
 using namespace ba;
 
 // Can the reduced system of this call go to the DMMA band solver (and therefore be streamed to it)?
+// The shared-memory tile solver takes the short systems (every window BA-Track really builds) and the bands the register
+// window of the band solver does not cover (half bandwidth 121 .. 145: the full-sequence Sintel window). Measured
+// (tools/solver_ab.py): 90 unknowns dense 28 us vs 39, 288 unknowns / bw 131 114 us vs 637 (scalar window solver);
+// from ~33 tile columns on a band <= 120 the band solver wins (378 unknowns: 113 us vs 134).
+constexpr int kTileSolverMaxCols = 32;
+static bool band_solver_covers(const CallView &cv) {
+  return cv.ld != cv.M && cv.bw <= kMmaMaxBw && solve_mma_smem_bytes(cv.M) <= 227 * 1024 - 64;
+}
+static bool tile_solver_applies(const BaPlan *pl, const CallView &cv) {
+  if (pl->opt.solver != 0 && pl->opt.solver != 4) return false;
+  if (!solve_tiles_applies(cv.M, cv.bw, nullptr)) return false;
+  return pl->opt.solver == 4 || (cv.M + 7) / 8 <= kTileSolverMaxCols || !band_solver_covers(cv);
+}
 static bool mma_solver_applies(const BaPlan *pl, const CallView &cv) {
-  const bool want_mma = pl->opt.solver == 0 || pl->opt.solver == 1;      // BA_OPT_SOLVER 2 / 3 force a fallback (tests, A/B timing)
-  return want_mma && cv.ld != cv.M && cv.bw <= kMmaMaxBw && solve_mma_smem_bytes(cv.M) <= 227 * 1024 - 64;
+  const bool want_mma = pl->opt.solver == 0 || pl->opt.solver == 1 || pl->opt.solver == 5;   // BA_OPT_SOLVER 2 / 3 / 4 force another one (tests, A/B timing)
+  if (tile_solver_applies(pl, cv)) return false;
+  return want_mma && band_solver_covers(cv);
 }
 static int launch_band_solver(const BaPlan *pl, const CallView &cv, int allow_retry, const SolveFeed &feed, cudaStream_t s) {
   return pl->opt.solver == 1 ? launch_solve_band_mma(cv, allow_retry, pl->Wg, feed, s) : launch_solve_band_diag(cv, allow_retry, pl->Wg, feed, s);
@@ -1443,7 +1457,10 @@ static int solve_update_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int
     if (!(pl->ev_mask & (1u << BA_STAGE_SOLVE))) BA_MARK(pl, BA_STAGE_SOLVE, s);
     const int WS = cv.bw + 1, WSP = WS | 1;
     const size_t smem = ((size_t)WS * WSP + cv.M + WS) * sizeof(double);
-    if (mma_solver_applies(pl, cv)) {
+    if (tile_solver_applies(pl, cv)) {
+      rc = launch_solve_tiles(cv, pb->monodisp ? 1 : 0, pl->Wg, (pl->opt.trace & 4) ? pl->trace_buf : nullptr, s);
+      if (rc) return rc;
+    } else if (mma_solver_applies(pl, cv)) {
       rc = launch_band_solver(pl, cv, pb->monodisp ? 1 : 0, make_feed(pl, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr), s);
       if (rc) return rc;
     } else if (cv.ld != cv.M && smem <= 227 * 1024 - 64 && pl->opt.solver != 3) {

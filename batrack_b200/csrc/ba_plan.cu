@@ -345,6 +345,7 @@ static int prepare_device(int dev, cudaStream_t s) {
   int rc = kernels_prepare_device();
   if (!rc) rc = solve_diag_prepare_device();
   if (!rc) rc = solve_mma_prepare_device(dev, s);
+  if (!rc) rc = solve_tiles_prepare_device();
   if (!rc) rc = schur_tc_prepare_device();
   if (!rc) g_dev_ready[dev] = true;
   return rc;
@@ -359,6 +360,8 @@ static void options_from_env(BaOptions *o) {
     if (e[0] == 'm' || e[0] == '1') o->solver = 1;
     else if (e[0] == 'w' || e[0] == '2') o->solver = 2;
     else if ((e[0] == 'd' && e[1] == 'e') || e[0] == '3') o->solver = 3;
+    else if (e[0] == 't' || e[0] == '4') o->solver = 4;
+    else if ((e[0] == 'd' && e[1] == 'i') || e[0] == '5') o->solver = 5;
   }
   o->stream = env_int("BA_STREAM", 0) ? 1 : 0;   // off: with the tensor-core Schur kernel the plain sequence is faster
   o->stream_smem_kb = std::max(0, env_int("BA_STREAM_SMEM_KB", 0));
@@ -419,7 +422,7 @@ static int alloc_workspace(BaPlan *pl) {
     BA_CUDA(own(pl, &pl->SY, need));
     BA_CUDA(own(pl, &pl->L, sf + 8));
     BA_CUDA(own(pl, &pl->dX, 6 * (size_t)n + 8));
-    BA_CUDA(own(pl, &pl->Wg, solve_mma_scratch_doubles(6 * n, std::min(bw, kMmaMaxBw)) + 64));   // solver scratch
+    BA_CUDA(own(pl, &pl->Wg, std::max(solve_mma_scratch_doubles(6 * n, std::min(bw, kMmaMaxBw)), solve_tiles_scratch_doubles(6 * n, bw)) + 64));   // solver scratch
     pl->sy_floats = need;
   }
   pl->info.banded = (ld != 6 * n) ? 1 : 0;
@@ -680,7 +683,7 @@ constexpr size_t kTraceValues = 16 * 4096 + 32;
 extern "C" int ba_plan_set_option(BaPlan *pl, int32_t key, int32_t value) {
   if (!pl) return BA_ERR_ARG;
   switch (key) {
-    case BA_OPT_SOLVER: if (value < 0 || value > 3) return BA_ERR_ARG; pl->opt.solver = value; break;
+    case BA_OPT_SOLVER: if (value < 0 || value > 5) return BA_ERR_ARG; pl->opt.solver = value; break;
     case BA_OPT_STREAM: pl->opt.stream = value ? 1 : 0; break;
     case BA_OPT_STREAM_SMEM_KB: if (value < 0 || value > 200) return BA_ERR_ARG; pl->opt.stream_smem_kb = value; break;
     case BA_OPT_SCHUR_TILE: if (value < 4) return BA_ERR_ARG; pl->opt.schur_tile = value & ~3; break;

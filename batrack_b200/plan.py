@@ -47,7 +47,7 @@ class Plan:
 
     def set_option(self, name, value):
         """Per-plan switch (BA_OPT_* in include/batrack_ba.h): solver, stream, stream_smem_kb, schur_tile, twist_min,
-        spin_cap, solver_trace, schur. `solver` also takes "diag" / "mma" / "window" / "dense"."""
+        spin_cap, solver_trace, schur. `solver` also takes "auto" / "diag" / "tiles" / "mma" / "window" / "dense"."""
         if name == "solver" and isinstance(value, str):
             value = _capi.SOLVERS[value]
         _capi.check(_capi.lib().ba_plan_set_option(self.handle, _capi.OPTIONS[name], int(value)), f"set_option({name})")

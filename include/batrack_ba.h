@@ -100,9 +100,12 @@ int ba_plan_set_layout(BaPlan *plan, int32_t n_total, int32_t block_bandwidth);
 /* Per-plan switches (defaults: the values below, or the environment variable of the same name without the
  * BA_OPT_ prefix — e.g. BA_SOLVER, BA_STREAM — read once when the plan is created). Returns BA_ERR_ARG for an
  * unknown key or an unsupported value. None of them changes results beyond summation order. */
-#define BA_OPT_SOLVER 1          /* 0 DMMA band solver, diagonal tile ownership (default); 1 DMMA band solver, circular
-                                    ownership (round-1 kernel); 2 scalar window Cholesky; 3 dense single-CTA Cholesky */
-#define BA_OPT_STREAM 2          /* 1 (default): ba_step starts the band solver next to the Schur kernel */
+#define BA_OPT_SOLVER 1          /* 0 automatic (default): shared-memory tile solver for short systems (< 64 tile columns, half
+                                    bandwidth <= 145), DMMA band solver with diagonal tile ownership for long bands, scalar
+                                    window / dense single-CTA Cholesky for the rest; 1 DMMA band solver, circular ownership
+                                    (round-1 kernel); 2 scalar window Cholesky; 3 dense single-CTA Cholesky; 4 tile solver
+                                    wherever it applies; 5 diagonal-ownership band solver wherever it applies */
+#define BA_OPT_STREAM 2          /* 1: ba_step starts the band solver next to the Schur kernel (default 0: the plain sequence is faster) */
 #define BA_OPT_STREAM_SMEM_KB 3  /* dynamic shared memory forced on the streamed Schur kernel (occupancy throttle; tests) */
 #define BA_OPT_SCHUR_TILE 4      /* tracks per cp.async stage of the SIMT Schur kernel (default 64) */
 #define BA_OPT_TWIST_MIN 5       /* tile columns (8 unknowns each) from which two CTAs eliminate from both ends (default 64) */

@@ -550,3 +550,38 @@ def test_ba_step_replays_from_a_cuda_graph(stream):
         Ge, pe = call()
         assert rel_err(Gr.cpu().numpy(), Ge.data.cpu().numpy()) < 1e-6
         assert rel_err(pr.cpu().numpy(), pe.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("n_kf", [12, 40])
+def test_every_band_solver_matches_the_oracle(n_kf):
+    """The reduced solve has four implementations behind BA_OPT_SOLVER (shared-memory tile solver: short systems and
+    bands up to 145; DMMA band solver: long bands up to 120; scalar window solver; automatic choice). On one graph they
+    must all land on the fp64 oracle's result, and a failed factorisation (ba.py:9-13) must leave the poses alone."""
+    from batrack_b200 import synth
+    from batrack_b200.ba import BA_rgbd_droid
+    from batrack_b200.lietorch import SE3
+    from batrack_b200.plan import Plan
+    from gpu_util import as_cuda
+    prob = synth.make_window_problem(n_kf, 64, 19, seed=11)
+    t = as_cuda(prob)
+    N, NM = t["poses"].shape[1], t["patches"].shape[1]
+    w = torch.from_numpy(prob.weights).cuda()[None]
+    P64, D64 = _oracle().run_sequence(prob, [prob.weights], [False], torch.float64, mode="sparse")
+    for sv in ("auto", "tiles", "diag", "window"):
+        plan = Plan(t["ii"], t["jj"], t["kk"], N, NM)
+        plan.set_option("solver", sv)
+
+        def call(ep):
+            return BA_rgbd_droid(SE3(t["poses"]), t["patches"], t["patches_monodisp"], t["intrinsics"], t["targets_2d"], None,
+                                 w, prob.lmbda, t["ii"], t["jj"], t["kk"], prob.bounds, ep=ep, fixedp=prob.fixedp,
+                                 loss=prob.loss, alpha=prob.alpha, plan=plan)
+
+        G, p = call(prob.ep)
+        assert plan.status() == 0, sv
+        assert rel_err(G.data[0].cpu().numpy(), P64[0]) < TOL, sv
+        assert rel_err(p[0, :, 2, 0, 0].cpu().numpy(), D64[0]) < TOL, sv
+        Gf, pf = call(-1e12)
+        assert plan.status() & 1, sv
+        assert rel_err(Gf.data.cpu().numpy(), t["poses"].cpu().numpy()) < 1e-6, sv
+        G2, _ = call(prob.ep)
+        assert plan.status() == 0 and rel_err(G2.data.cpu().numpy(), G.data.cpu().numpy()) < 1e-6, sv

@@ -15,7 +15,9 @@ from batrack_b200.plan import Plan
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 solvers = sys.argv[2].split(",") if len(sys.argv) > 2 else ["diag", "mma"]
-if name == "davis":
+if name == "sintel":
+    prob, _ = synth.make_slam_problem(n_frames=50, patches_per_frame=256, seed=4, buffer_size=64, opt_window=64, removal_window=64, width=1024, height=436, name="sintel_like")
+elif name == "davis":
     prob, _ = synth.make_slam_problem(n_frames=25, patches_per_frame=400, seed=7, buffer_size=64)
 else:
     prob = synth.make_config(name)
@@ -31,7 +33,7 @@ def call(plan):
 
 ref = None
 for sv in solvers:
-    for stream in (0, 1):
+    for stream in (0,):
         plan = Plan(t["ii"], t["jj"], t["kk"], N, NM)
         plan.set_option("solver", sv)
         plan.set_option("stream", stream)
@@ -52,6 +54,15 @@ for sv in solvers:
         err = np.abs(dX - ref).max() / max(np.abs(ref).max(), 1e-30)
         print(f"{name} solver={sv} stream={stream}: " + " ".join(f"{a} {b * 1e3:.1f}" for a, b in acc.items()) +
               f" | sum {sum(acc.values()) * 1e3:.1f} us | status {st} | dX vs first {err:.2e}", flush=True)
+        if sv == "tiles":
+            plan.enable_timing(False)
+            plan.set_option("solver_trace", 4)
+            call(plan)
+            nt = (6 * n + 7) // 8
+            h = plan.read_trace()[:16 * 4096].reshape(4096, 16)[1:nt - 2].astype(np.float64)
+            m = lambda x: float(x.mean())
+            print(f"   tiles trace ({nt} tile columns): [P] {m(h[:, 1] - h[:, 0]):.0f} barrier {m(h[:, 2] - h[:, 1]):.0f} | warp 0: update {m(h[:, 3] - h[:, 2]):.0f} factor {m(h[:, 4] - h[:, 3]):.0f} "
+                  f"wait {m(h[:, 5] - h[:, 4]):.0f} | warp 5: pairs {m(h[:, 9] - h[:, 8]):.0f} | warp 4: row load {m(h[:, 13] - h[:, 12]):.0f} | step {m(h[1:, 0] - h[:-1, 0]):.0f}")
         if stream == 0 and sv in ("diag", "mma"):
             plan.enable_timing(False)
             plan.set_option("solver_trace", 1)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-stage device times (library CUDA events) of one BA call on a named workload: cfg3 | mid | davis."""
+"""Per-stage device times (library CUDA events) of one BA call on a named workload: cfg3 | mid | davis | sintel."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,6 +11,9 @@ from batrack_b200.plan import Plan
 name = sys.argv[1] if len(sys.argv) > 1 else "davis"
 if name == "davis":
     prob, w_all = synth.make_slam_problem(n_frames=25, patches_per_frame=400, seed=7, buffer_size=64)
+elif name == "sintel":
+    prob, w_all = synth.make_slam_problem(n_frames=50, patches_per_frame=256, seed=4, buffer_size=64, opt_window=64,
+                                          removal_window=64, width=1024, height=436, name="sintel_like")
 else:
     prob = synth.make_config(name); w_all = prob.weights
 t = {k: v.cuda() for k, v in prob.as_torch().items()}
