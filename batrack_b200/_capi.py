@@ -36,6 +36,9 @@ _P, _I64, _I32 = C.c_void_p, C.c_int64, C.c_int32
 SYMBOLS = {
     "ba_plan_create": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, C.POINTER(_P)]),
     "ba_plan_destroy": (None, [_P]),
+    "ba_plan_create_capacity": (C.c_int, [_I64, _I32, _I32, _I32, _I64, _I32, _I32, _P, C.POINTER(_P)]),
+    "ba_plan_update": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P]),
+    "ba_plan_finalize": (C.c_int, [_P]),
     "ba_plan_info": (C.c_int, [_P, C.POINTER(BaPlanInfo)]),
     "ba_plan_set_layout": (C.c_int, [_P, _I32, _I32]),
     "ba_plan_set_option": (C.c_int, [_P, _I32, _I32]),

@@ -21,6 +21,8 @@ def _problem(plan, poses, patches, monodisp, intrinsics, targets, weights, lmbda
              structure_only, loss, alpha):
     if loss not in _capi.LOSS_IDS:
         raise NotImplementedError(loss)                                   # ba.py:98-99
+    if getattr(plan, "_stale", False):
+        plan.finalize()                                                   # CapacityPlan.update(): read its counts now
     pdata = poses.data
     b, N = pdata.shape[0], pdata.shape[1]
     if b != 1:

@@ -330,6 +330,7 @@ extern "C" int ba_stage_host_async(BaPlan *pl, const BaProblem *ph, BaProblem *p
     return BA_ERR_ARG;
   if (ph->targets_stride != 0 && ph->targets_stride != 2) return BA_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream_;
+  if (int rc = ba::plan_finalize(pl)) return rc;
   const size_t N = pl->v.N, NM = pl->v.NM, E = (size_t)pl->v.E, m = pl->v.m;
   const size_t f = sizeof(float);
   auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };

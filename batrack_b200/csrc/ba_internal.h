@@ -108,8 +108,42 @@ struct BaOptions {
   int schur_acc;       // BA_OPT_SCHUR_ACC: chunks of 32 tracks accumulated in TMEM (fp32) before the fp64 read-back
 };
 
+// Capacities of a plan's arrays. ba_plan_create sizes them exactly (one read-back between the two halves of the build); a
+// capacity plan (ba_plan_create_capacity) is sized once for the largest graph the caller will ever hand to ba_plan_update.
+struct BaCaps { int64_t E; int m, G, pat, units[4]; int64_t est; };
+// host-chosen overrides of the derived unit lengths (environment, experiments): -1 = derive on device
+struct BaTuning { int tc, tu, kp, to, gend; };
+// Everything the device-side build of a plan writes (ba_plan.cu): plan arrays (the PlanView points into them), build
+// scratch, the shape block and its pinned host copy.
+struct PlanBuild {
+  BaCaps caps;
+  BaTuning tun;
+  int front_G;                         // capacity of the front half's group arrays (>= caps.G)
+  unsigned *key, *skey, *eij, *sij;
+  int *val, *tflag, *tinc, *gflag, *ginc, *g_d, *maxo;
+  int4 *cflag, *cinc;
+  long long *g_esz, *g_eoff;
+  char *cub_tmp;
+  size_t cub_bytes;
+  int *eperm, *kx, *tptr, *t_grp, *g_t0, *g_pat, *g_W, *g_reg, *g_nm;
+  int *pat_i, *pat_j, *pat_li, *pat_lj, *pat_ri, *pat_rj, *pat_ps, *slot_pose, *slot_ptr, *slot_items, *ms_ptr, *ms_slot;
+  int *unit_t0[4], *unit_grp[4], *order, *top_need, *bot_need, *patch_track;
+  ba::ChunkDesc *cdesc;
+  int *shape_dev, *shape_host;
+  cudaEvent_t ev_shape;
+  const void *g_key[4];                // (ii, jj, kk, n_edges_dev) of the last ba_plan_update and, when they repeat,
+  int64_t g_n;                         // the captured graph of the whole derivation
+  cudaGraphExec_t g_exec;
+  cudaStream_t g_stream;
+  cudaEvent_t g_ev_in;
+  int g_failed;
+  int pending;                         // a build is in flight: the host has not read its shape block yet
+  int valid;                           // the plan describes a graph
+};
+
 struct BaPlan {
   BaPlanInfo info;
+  PlanBuild b;
   BaOptions opt;
   long long *trace_buf;
   ba::PlanView v;
@@ -145,6 +179,8 @@ struct BaPlan {
 namespace ba {
 extern std::atomic<long long> g_launches;
 int set_cuda_error(cudaError_t e, const char *what);
+// host side of a finished plan build: waits for the shape block of a pending ba_plan_update (no-op otherwise)
+int plan_finalize(BaPlan *pl);
 void layout_for(const BaPlan *p, int fixedp, int *n, int *bw, int *ld, int *off, int64_t *s_floats);
 constexpr int kMmaMaxBw = 120;        // widest band the 16x16-tile register window of the DMMA solver covers
 size_t solve_mma_smem_bytes(int M);

@@ -1288,6 +1288,7 @@ __global__ void k_debug_cast(const double *in, float *out, int n) {
 static int make_call(BaPlan *pl, const BaProblem *pb, CallView *cv) {
   if (!pl || !pb || !pb->poses || !pb->patches || !pb->intrinsics || !pb->targets || !pb->weights) return BA_ERR_ARG;
   if (pb->fixedp < 0 || pb->loss < 0 || pb->loss > 2) return BA_ERR_ARG;
+  if (int rc = plan_finalize(pl)) return rc;                       // a pending ba_plan_update: wait for its shape block
   std::memset(cv, 0, sizeof(*cv));
   cv->poses = pb->poses; cv->patches = pb->patches; cv->monodisp = pb->monodisp; cv->intr = pb->intrinsics;
   cv->targets = pb->targets; cv->weights = pb->weights; cv->lmbda_vec = pb->lmbda_vec;

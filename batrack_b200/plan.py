@@ -101,6 +101,55 @@ class Plan:
         return int(_tensor_view(p.value, 1, self.device, self, dtype=torch.int32).item())
 
 
+class CapacityPlan(Plan):
+    """A plan allocated once for the largest graph a SLAM session will build. `update(ii, jj, kk)`
+    re-derives it for the current graph on the device — no host synchronisation, no allocation; the counts come back
+    through pinned memory and are read by the first BA call that uses the plan (`finalize()` does it explicitly).
+
+    cap_groups: tracks with identical (ii, jj) lists form a group — one per source keyframe in BA-Track's graphs
+    (main/batrack.py:399-410), so the number of frames that can source edges bounds it; cap_pattern bounds the sum over
+    groups of the edges of one track. A graph that does not fit raises RuntimeError("...capacity...") at first use."""
+
+    def __init__(self, n_poses, n_patches, cap_edges, cap_tracks=None, cap_groups=None, cap_pattern=None, cap_est=0,
+                 device="cuda"):
+        self.device = torch.device(device if isinstance(device, str) and ":" in device else torch.device(device, torch.cuda.current_device())
+                                   if str(device) == "cuda" else device)
+        cap_tracks = int(cap_tracks if cap_tracks is not None else min(cap_edges, n_patches))
+        cap_groups = int(cap_groups if cap_groups is not None else min(cap_tracks, 4 * n_poses))
+        cap_pattern = int(cap_pattern if cap_pattern is not None else min(cap_edges, 256 * cap_groups))
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = _capi.lib().ba_plan_create_capacity(int(cap_edges), cap_tracks, cap_groups, cap_pattern, int(cap_est),
+                                                     int(n_poses), int(n_patches), _capi.stream_ptr(self.device), C.byref(handle))
+        _capi.check(rc, "ba_plan_create_capacity")
+        self.handle = handle
+        self.info = _capi.BaPlanInfo()
+        self._keep = ()
+        self.layout_n_total = 0
+
+    def update(self, ii, jj, kk, n_edges_dev=None):
+        """Enqueue the re-derivation for (ii, jj, kk) on the current stream. n_edges_dev: optional int32 CUDA tensor with
+        the live edge count (<= len(ii)) when the graph is maintained on the device."""
+        for name, t in (("ii", ii), ("jj", jj), ("kk", kk)):
+            if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.int64 or not t.is_contiguous():
+                raise RuntimeError(f"{name}: contiguous int64 CUDA tensor required")
+        self._keep = (ii, jj, kk, n_edges_dev)
+        with torch.cuda.device(self.device):
+            rc = _capi.lib().ba_plan_update(self.handle, _capi.ptr(ii), _capi.ptr(jj), _capi.ptr(kk), ii.numel(),
+                                            _capi.ptr(n_edges_dev) if n_edges_dev is not None else None,
+                                            _capi.stream_ptr(self.device))
+        _capi.check(rc, "ba_plan_update")
+        self._stale = True
+        return self
+
+    def finalize(self):
+        _capi.check(_capi.lib().ba_plan_finalize(self.handle), "ba_plan_finalize")
+        _capi.check(_capi.lib().ba_plan_info(self.handle, C.byref(self.info)), "ba_plan_info")
+        self.layout_n_total = self.info.n_total
+        self._stale = False
+        return self
+
+
 class _RawCuda:
     """__cuda_array_interface__ carrier for memory owned by the C library."""
 

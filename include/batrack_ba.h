@@ -37,6 +37,7 @@ extern "C" {
 #define BA_ERR_INDEX_RANGE (-3)   /* an edge index is outside [0,N) / [0,NM) */
 #define BA_ERR_TOO_MANY_POSES (-4)/* N > 65535 (pose indices are packed to 16 bits) */
 #define BA_ERR_NO_DEVICE (-5)     /* no sm_100 device / kernel image not loadable */
+#define BA_ERR_CAPACITY (-6)      /* the graph handed to ba_plan_update exceeds a capacity of the plan */
 
 #define BA_LOSS_TRIVIAL 0         /* compute_kernel_weight, main/backend/ba.py:81-100 */
 #define BA_LOSS_HUBER 1
@@ -92,6 +93,24 @@ int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_t *kk, int6
                    int32_t n_poses, int32_t n_patches, void *stream, BaPlan **out);
 void ba_plan_destroy(BaPlan *plan);
 int ba_plan_info(const BaPlan *plan, BaPlanInfo *out);
+
+/* Factor-graph maintenance without host synchronisation (replaces the per-frame plan rebuild behind
+ * main/batrack.py:189-212 append_factors / remove_factors, :399-410 __edges, :1023-1073 keyframe).
+ * ba_plan_create_capacity allocates a plan ONCE for the largest graph the caller will hand over: cap_edges edges,
+ * cap_tracks patches with edges, cap_groups pattern groups (tracks with identical (ii,jj) lists: one per source keyframe in a
+ * SLAM graph), cap_pattern pattern positions (sum over groups of the edges of one track), cap_est floats of per-track E
+ * storage (0: 6 * (cap_edges + 4 * cap_tracks)). It describes no graph yet.
+ * ba_plan_update re-derives the whole plan for a new (ii,jj,kk) ON THE DEVICE: ~35 kernel launches and one asynchronous
+ * copy of the shape block (counts) to pinned host memory on `stream` — no synchronisation, no allocation. The counts are
+ * read by the first call that uses the plan (or by ba_plan_finalize), which waits for that copy only. n_edges is an upper
+ * bound of the edge count; n_edges_dev (device memory, may be NULL) holds the live count when the caller keeps it on the
+ * device. The index arrays must stay valid until then. Returns BA_ERR_CAPACITY (from the call that finalizes) when the
+ * graph does not fit: build an exact plan with ba_plan_create instead. */
+int ba_plan_create_capacity(int64_t cap_edges, int32_t cap_tracks, int32_t cap_groups, int32_t cap_pattern, int64_t cap_est,
+                            int32_t n_poses, int32_t n_patches, void *stream, BaPlan **out);
+int ba_plan_update(BaPlan *plan, const int64_t *ii, const int64_t *jj, const int64_t *kk, int64_t n_edges,
+                   const int32_t *n_edges_dev, void *stream);
+int ba_plan_finalize(BaPlan *plan);
 
 /* Sharded graphs: make n_total / block_bandwidth agree across ranks so that every
  * rank lays the reduced camera system out identically. Pass the max over ranks. */
