@@ -112,6 +112,30 @@ int ba_plan_update(BaPlan *plan, const int64_t *ii, const int64_t *jj, const int
                    const int32_t *n_edges_dev, void *stream);
 int ba_plan_finalize(BaPlan *plan);
 
+/* The factor graph itself on the device: edge list (ii, jj, kk) + the per-edge payload the caller keeps next to it
+ * (targets_3d [E,3], weights [E,2], weights_pose [E,2]) in fixed capacity buffers, the live edge count in device memory.
+ * Every operation is a few launches on `stream`, none synchronises; the buffers never move.
+ *   ba_graph_append  main/batrack.py:189-204 append_factors: n edges (kk = patch[e], jj = frame[e], ii = ix[patch[e]]) with
+ *                    their payload rows (NULL: zeros), appended behind the live edges
+ *   ba_graph_remove  stable removal, payload included (main/batrack.py:206-212 remove_factors):
+ *                    mode 0  mask[e] != 0                                  (any caller-computed mask, uint8 [n_upper])
+ *                    mode 1  ix[kk[e]] < a                                 (:1023-1026, :1072-1073 removal window)
+ *                    mode 2  ii[e] == a || jj[e] == a, then kk[ii > a] -= patches_per_frame, ii[ii > a] -= 1, jj[jj > a] -= 1
+ *                                                                          (:1042-1051 keyframe())
+ *   ba_graph_arrays  device pointers, the device-side count and the host's upper bound of it (what ba_plan_update takes)
+ *   ba_graph_count   the live count (synchronises `stream`);  ba_graph_tighten: tell the graph a count learned elsewhere */
+typedef struct BaGraph BaGraph;
+int ba_graph_create(int64_t cap_edges, void *stream, BaGraph **out);
+void ba_graph_destroy(BaGraph *graph);
+int ba_graph_arrays(const BaGraph *graph, int64_t **ii, int64_t **jj, int64_t **kk, float **targets_3d, float **weights,
+                    float **weights_pose, int32_t **n_edges_dev, int64_t *n_edges_upper, int64_t *capacity);
+int ba_graph_append(BaGraph *graph, const int64_t *patch, const int64_t *frame, int64_t n, const int64_t *ix,
+                    const float *targets_3d, const float *weights, const float *weights_pose, void *stream);
+int ba_graph_remove(BaGraph *graph, int32_t mode, int64_t a, int64_t patches_per_frame, const uint8_t *mask, const int64_t *ix,
+                    void *stream);
+int ba_graph_count(BaGraph *graph, int64_t *n_edges, void *stream);
+int ba_graph_tighten(BaGraph *graph, int64_t n_edges);
+
 /* Sharded graphs: make n_total / block_bandwidth agree across ranks so that every
  * rank lays the reduced camera system out identically. Pass the max over ranks. */
 int ba_plan_set_layout(BaPlan *plan, int32_t n_total, int32_t block_bandwidth);

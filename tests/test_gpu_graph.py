@@ -104,3 +104,65 @@ def test_plan_update_uses_the_device_side_edge_count():
     ref = Plan(*[torch.from_numpy(a[:live]).to(dev) for a in (ii, jj, kk)], N, N * M)
     assert cplan.info.n_edges == live == ref.info.n_edges
     assert cplan.info.n_groups == ref.info.n_groups and torch.equal(cplan.tracks(), ref.tracks())
+
+
+def test_device_factor_graph_replays_the_reference_bookkeeping():
+    """FactorGraph (ba_graph_*): append_factors / removal window / keyframe() edge surgery / arbitrary masks on the device
+    against the same operations in numpy (the reference's torch.cat / boolean-mask code, main/batrack.py:189-212,
+    1042-1051, 1072-1073), payload rows included; the plan derived from the device-resident graph equals a plan built from
+    scratch on the host's copy."""
+    from batrack_b200.graph import FactorGraph
+    from batrack_b200.plan import Plan
+    dev = torch.device("cuda:0")
+    n_frames, M, N, s_slam, stride, removal = 23, 64, 32, 12, 2, 14
+    rng = np.random.default_rng(3)
+    # a random mask breaks the "one pattern group per keyframe" structure: room for one group per track
+    fg = FactorGraph(N, M, cap_edges=200000, cap_groups=N * M, cap_pattern=200000, device=dev)
+    ix = torch.arange(N * M, device=dev) // M                                   # patch -> source frame (self.ix)
+    ii = jj = kk = np.zeros(0, dtype=np.int64)
+    tg, w, wp = np.zeros((0, 3), np.float32), np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32)
+    n = 0
+
+    def check(tag):
+        gi, gj, gk, gt, gw, gwp = fg.edges()
+        assert gi.numel() == ii.shape[0], (tag, gi.numel(), ii.shape[0])
+        for a, b in ((gi, ii), (gj, jj), (gk, kk), (gt, tg), (gw, w), (gwp, wp)):
+            assert np.array_equal(a.cpu().numpy(), b), tag
+
+    for step in range(2, n_frames + 1):
+        n = step
+        if (step - 1) % stride == 0:
+            lo = max(step - s_slam, 0)
+            kf = np.arange(lo, step, stride)
+            pk = (kf[:, None] * M + np.arange(M)[None, :]).reshape(-1)
+            fr = np.arange(lo, step)
+            k_new, j_new = np.repeat(pk, fr.shape[0]), np.tile(fr, pk.shape[0])
+            t_new = rng.normal(size=(k_new.shape[0], 3)).astype(np.float32)
+            w_new = rng.uniform(size=(k_new.shape[0], 2)).astype(np.float32)
+            wp_new = rng.uniform(size=(k_new.shape[0], 2)).astype(np.float32)
+            c = lambda a: torch.from_numpy(a).to(dev)
+            fg.append_factors(c(k_new), c(j_new), ix, c(t_new), c(w_new), c(wp_new))
+            ii = np.concatenate([ii, k_new // M]); jj = np.concatenate([jj, j_new]); kk = np.concatenate([kk, k_new])
+            tg, w, wp = np.concatenate([tg, t_new]), np.concatenate([w, w_new]), np.concatenate([wp, wp_new])
+        if step == 15:                                                          # keyframe(): frame k leaves the window
+            k = step - 4
+            keep = ~((ii == k) | (jj == k))
+            ii, jj, kk, tg, w, wp = ii[keep], jj[keep], kk[keep], tg[keep], w[keep], wp[keep]
+            kk = np.where(ii > k, kk - M, kk); ii = np.where(ii > k, ii - 1, ii); jj = np.where(jj > k, jj - 1, jj)
+            fg.remove_keyframe(k)
+        if step == 18:                                                          # an arbitrary mask
+            m = rng.uniform(size=fg.n_upper) < 0.1
+            live = m[:ii.shape[0]]
+            ii, jj, kk, tg, w, wp = ii[~live], jj[~live], kk[~live], tg[~live], w[~live], wp[~live]
+            fg.remove_factors(torch.from_numpy(m).to(dev))
+        keep = ii >= n - removal                                                # removal window
+        ii, jj, kk, tg, w, wp = ii[keep], jj[keep], kk[keep], tg[keep], w[keep], wp[keep]
+        fg.remove_before(n - removal, ix)
+        if step % 3 == 0 or step == n_frames:
+            plan = fg.plan()                                                    # enqueued; finalized by edges()
+            check(step)
+            ref = Plan(*[torch.from_numpy(a).to(dev) for a in (ii, jj, kk)], N, N * M)
+            for f in ("n_edges", "n_total", "n_tracks", "n_groups", "n_chunks", "max_degree", "max_slots", "block_bandwidth"):
+                assert getattr(plan.info, f) == getattr(ref.info, f), (step, f)
+            assert torch.equal(plan.tracks(), ref.tracks())
+    assert ii.shape[0] > 10000
