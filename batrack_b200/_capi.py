@@ -39,6 +39,7 @@ SYMBOLS = {
     "ba_plan_create_capacity": (C.c_int, [_I64, _I32, _I32, _I32, _I64, _I32, _I32, _P, C.POINTER(_P)]),
     "ba_plan_update": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P]),
     "ba_plan_finalize": (C.c_int, [_P]),
+    "ba_trajectory": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P]),
     "ba_graph_create": (C.c_int, [_I64, _P, C.POINTER(_P)]),
     "ba_graph_destroy": (None, [_P]),
     "ba_graph_arrays": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),

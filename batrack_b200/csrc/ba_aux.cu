@@ -424,3 +424,55 @@ extern "C" int ba_step_host(BaPlan *pl, const BaProblem *ph, void *stream_) {
   if (rc) return rc;
   return ba_host_sync(pl, stream_, 1);
 }
+
+// ---- trajectory hand-off: main/batrack.py:223-228 get_pose, :898-915 terminate, :1080-1088 get_results.
+// Frame t is either a keyframe (slot[t] >= 0: its pose sits in the pose buffer) or was dropped by keyframe() and carries
+// delta[t] = (t0, dP): pose(t) = dP * pose(t0), recursively. One thread per frame walks its chain, composes it,
+// inverts (world-from-camera) and writes the 7-vector in terminate()'s order [tx ty tz qw qx qy qz] and / or the 4x4
+// matrix get_results() stores as cams_T_world.
+namespace ba {
+__global__ void k_trajectory(const float *__restrict__ poses, const int *__restrict__ slot, const int *__restrict__ t0,
+                             const float *__restrict__ dP, int T, int max_chain, float *__restrict__ out7, float *__restrict__ out44,
+                             int *__restrict__ err) {
+  namespace g = se3t;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  // chain length first, then compose from the keyframe outwards — the order of the reference's recursion
+  // (get_pose(t) = dP_t * get_pose(t0)), so the roundings agree
+  int cur = t, L = 0;
+  while (slot[cur] < 0) {
+    cur = t0[cur];
+    if (cur < 0 || cur >= T || ++L > max_chain) { atomicOr(err, 1); return; }   // a frame with neither pose nor delta
+  }
+  g::P<float> X = g::load(poses + 7 * (size_t)slot[cur]);
+  for (int k = L - 1; k >= 0; --k) {
+    int c = t;
+    for (int s2 = 0; s2 < k; ++s2) c = t0[c];
+    X = g::mul(g::load(dP + 7 * (size_t)c), X);
+  }
+  X = g::inv(X);
+  if (out7) {
+    float *o = out7 + 7 * (size_t)t;
+    o[0] = X.t.x; o[1] = X.t.y; o[2] = X.t.z; o[3] = X.q.w; o[4] = X.q.x; o[5] = X.q.y; o[6] = X.q.z;   // batrack.py:908
+  }
+  if (out44) {
+    float R[9];
+    g::qmatrix(X.q, R);
+    float *m = out44 + 16 * (size_t)t;
+    m[0] = R[0]; m[1] = R[1]; m[2] = R[2]; m[3] = X.t.x;
+    m[4] = R[3]; m[5] = R[4]; m[6] = R[5]; m[7] = X.t.y;
+    m[8] = R[6]; m[9] = R[7]; m[10] = R[8]; m[11] = X.t.z;
+    m[12] = 0.f; m[13] = 0.f; m[14] = 0.f; m[15] = 1.f;
+  }
+}
+}  // namespace ba
+
+extern "C" int ba_trajectory(const float *poses, const int32_t *slot, const int32_t *t0, const float *dP, int32_t n_frames,
+                             float *out7, float *out44, int32_t *err, void *stream) {
+  if (n_frames < 0) return BA_ERR_ARG;
+  if (n_frames == 0) return BA_OK;
+  if (!poses || !slot || !t0 || !dP || !err || (!out7 && !out44)) return BA_ERR_ARG;
+  ba::k_trajectory<<<(n_frames + 127) / 128, 128, 0, (cudaStream_t)stream>>>(poses, slot, t0, dP, n_frames, n_frames, out7, out44, err);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}

@@ -296,6 +296,14 @@ int ba_version(void);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t ba_launch_count(void);
 
+/* Trajectory hand-off (main/batrack.py:223-228 get_pose, :898-915 terminate, :1080-1088 get_results): frame t of the
+ * n_frames processed so far is a keyframe (slot[t] >= 0: row of `poses` [N,7]) or was dropped by keyframe() and carries
+ * delta[t] = (t0[t], dP[t] [7]) with pose(t) = dP[t] * pose(t0[t]). Writes the inverted (world-from-camera) poses as
+ * [tx ty tz qw qx qy qz] rows (out7, terminate()) and / or as 4x4 matrices (out44, cams_T_world); either may be NULL.
+ * err (device int32) gets bit 0 when a frame has neither a pose nor a resolvable delta chain. */
+int ba_trajectory(const float *poses, const int32_t *slot, const int32_t *t0, const float *dP, int32_t n_frames,
+                  float *out7, float *out44, int32_t *err, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,3 +129,55 @@ def test_se3_identities_in_fp64():
     assert torch.allclose((Xs.adj(u) * w).sum(-1), (u * Xs.adjT(w)).sum(-1), atol=1e-8)
     # fp64 and fp32 kernels agree to fp32 rounding
     assert rel_err(Xs.to(torch.float32).adjT(w.float()).cpu().numpy(), Xs.adjT(w).cpu().numpy()) < 1e-5
+
+
+def test_trajectory_handoff_matches_the_reference_recursion():
+    """terminate() / get_results() (main/batrack.py:898-915, 1080-1088): every frame's pose through get_pose's recursion
+    (:223-228), inverted; one kernel against the same recursion spelled out with the CUDA SE3 ops in fp64
+    (themselves pinned on the reference by test_se3_identities_in_fp64 / the se3_ops fixture), including chains of dropped keyframes and the results dictionary's keys."""
+    import pickle, tempfile
+    from batrack_b200 import lietorch
+    from batrack_b200.lietorch import SE3
+    from batrack_b200.results import get_results, terminate, trajectory
+    rng = np.random.default_rng(5)
+    counter, N = 40, 48
+    kf_frames = [t for t in range(counter) if t % 3 == 0 or t > 33]          # frames still in the keyframe buffer
+    n = len(kf_frames)
+    xi = rng.normal(size=(N, 6)) * np.array([0.3] * 3 + [0.2] * 3)
+    poses = SE3.exp(torch.from_numpy(xi).float().cuda()).data.clone()
+    poses[:, 3:] *= torch.from_numpy(rng.uniform(0.7, 1.4, size=(N, 1))).float().cuda()    # un-normalised quaternions
+    tstamps = torch.zeros(N, dtype=torch.int64)
+    tstamps[:n] = torch.tensor(kf_frames)
+    delta = {}
+    for t in range(counter):
+        if t not in kf_frames:                                                # dropped: attached to the frame before
+            d = SE3.exp(torch.from_numpy(rng.normal(size=(1, 6)) * 0.05).float().cuda()).data
+            delta[t] = (t - 1, SE3(d[0]))
+    out7, cams = trajectory(poses, tstamps, n, delta, counter)
+    # the reference's code path, with the fp64 CUDA ops
+    traj = {int(tstamps[i]): poses[i].double() for i in range(n)}
+
+    def get_pose(t):
+        if t in traj:
+            return SE3(traj[t])
+        t0, dP = delta[t]
+        return SE3(dP.data.double()) * get_pose(t0)
+
+    ref = lietorch.stack([get_pose(t) for t in range(counter)], dim=0).inv()
+    ref7 = ref.data.cpu().numpy()[:, [0, 1, 2, 6, 3, 4, 5]]
+    assert np.abs(out7.cpu().numpy() - ref7).max() < 2e-6 * max(1.0, np.abs(ref7).max())
+    assert np.abs(cams.cpu().numpy() - ref.matrix().cpu().numpy()).max() < 2e-6 * max(1.0, np.abs(ref7).max())
+    p7, ts = terminate(poses, tstamps, n, delta, counter, list(range(counter)))
+    assert p7.shape == (counter, 7) and ts.dtype == np.float64
+    M, S = 8, 5
+    z = lambda *s: torch.zeros(*s).cuda()
+    with tempfile.NamedTemporaryFile(suffix=".pkl") as f:
+        res = get_results(poses, tstamps, n, delta, counter, list(range(counter)), z(N, 4), torch.ones(N, M).cuda(), z(N, M, S, 3),
+                          torch.ones(N, M, S, 1).cuda(), z(N, M, S, 1), z(N, M, S, 1), save_path=f.name)
+        back = pickle.load(open(f.name, "rb"))
+    assert sorted(res) == sorted(["cams_T_world", "intrinsics", "tstamps", "trajs_2d_disp", "trajs_valid", "trajs_static", "trajs_vis",
+                                  "grid_query_frames", "dmaps", "rgbs", "dmaps_gt"])
+    assert back["cams_T_world"].shape == (counter, 4, 4) and back["trajs_valid"].shape == (counter, M)
+    delta.pop(1)                                                              # frame 1 now has neither pose nor delta
+    with pytest.raises(KeyError):
+        trajectory(poses, tstamps, n, delta, counter)
