@@ -147,7 +147,10 @@ __global__ void k_derive(const int *__restrict__ g_pat, int cap_G, int cap_pat, 
   // edge pass: about one wave of CTAs (2 resident per SM) — per-CTA set-up and flush are amortised over more tracks;
   // Schur: units of <= 128 tracks, or whole 256-track groups (measured 4 us faster than two 128-track units at cfg3)
   int tc = min(256, max(8, cdiv(m, sms)));
-  int tu = min(256, max(16, 16 * cdiv(cdiv(m, 2 * sms), 16)));
+  // Schur units: ~128 of them when the graph allows units of >= 96 tracks (the tensor-core kernel's territory: its flush
+  // costs the same whatever the unit's length, so long units and about one per SM), shorter units for small graphs (SIMT
+  // kernel). Measured: 64 KF x 256 tracks 31 us with 56-track units, 19 us with 128; a 2-GPU shard of cfg3 63 -> ~20 us
+  int tu = min(256, max(16, 16 * cdiv(cdiv(m, 128), 16)));
   if (tu > 128) tu = 256;
   if (tun.tc > 0) tc = tun.tc;
   if (tun.tu > 0) tu = tun.tu;
