@@ -308,6 +308,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_schur_tc(PlanView pv, CallVie
     TC_TR(2);
     mbar_wait(&s_done, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // every converter warp arrived on `full` for the last chunk before `done` could fire, so the operand / raw stages are
+    // dead here; the named barrier states it in a form tools understand, too (racecheck does not follow mbarriers)
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kTcConvWarps) : "memory");
     TC_TR(3);
     const int lq = warp & 3, hcol = warp >> 2;
     const bool two = half < nch;

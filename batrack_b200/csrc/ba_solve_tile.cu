@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_solve_tiles(CallView cv, int 
         }
       double zr[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) zr[k] = z[8 * Jc + k];
+      for (int k = 0; k < 8; ++k) zr[k] = lane == 8 ? z[8 * Jc + k] : 0.0;     // (lane 8 alone reads and later rewrites the block of z)
       bool ok = true;
       double wv[8];
 #pragma unroll
