@@ -545,7 +545,9 @@ def main():
                            "peak": 37.0, "peak_source": "fp64 DFMA = DMMA peak measured with tools/microbench.cu (profiles/r01_microbench.txt)",
                            "frac": solve_flops / (solve_ms * 1e-3) / 1e12 / 37.0 if solve_ms > 0 else None,
                            "sms_used": 2, "dmma_pipe_pct_on_its_sms": prof.get("k_solve_band_diag", {}).get("fp64_pipe_pct"),
-                           "note": "with the streaming hand-over `solve` is the part of the solver left after the Schur kernel ended"},
+                           "note": "per-launch duration from the library's CUDA events on the launch stream (streaming hand-over off: the whole kernel); M * bw^2 flops of the band factorisation; the kernel is bound by the dependent chain of the factorisation (DESIGN.md §4 K3), not by the FP64 pipe"},
+        "tensor_core": {"kernel": "k_schur_tc (tcgen05.mma kind::tf32, 3xTF32, TMEM accumulators)", "kernel_ms": stages.get("schur", 0.0),
+                        "tensor_pipe_pct": prof.get("k_schur_tc", {}).get("tensor_pipe_pct"), "source": "profiles/r02_kernels.txt, profiles/r02_sass.txt"},
         "kernels": {k: {"ms": v, "share": v / tot} for k, v in stages.items()},
     }
     if world == 1 and wl == "cfg3":
