@@ -65,6 +65,7 @@ SYMBOLS = {
     "ba_plan_last_timing": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "ba_step_host": (C.c_int, [_P, C.POINTER(BaProblem), _P]),
     "ba_step_host_async": (C.c_int, [_P, C.POINTER(BaProblem), _P]),
+    "ba_prefetch_host_async": (C.c_int, [_P, C.POINTER(BaProblem), _P]),
     "ba_stage_host_async": (C.c_int, [_P, C.POINTER(BaProblem), C.POINTER(BaProblem), _P]),
     "ba_unstage_host_async": (C.c_int, [_P, C.POINTER(BaProblem), C.POINTER(BaProblem), _P]),
     "ba_host_sync": (C.c_int, [_P, _P, C.c_int]),

@@ -301,7 +301,10 @@ struct HostPipe {
   char *stage[2] = {nullptr, nullptr};
   size_t bytes = 0;
   unsigned long long seq = 0;
+  unsigned pre_mask = 0;         // inputs of call `seq` that ba_prefetch_host_async has already put on the upload stream
+  bool pre_waited = false;       // ... which has waited for the slot's previous user then
 };
+enum { PRE_MONO = 1, PRE_INTR = 2, PRE_TG = 4, PRE_W = 8, PRE_LAM = 16 };
 
 void host_pipe_destroy(void *p_) {
   HostPipe *p = static_cast<HostPipe *>(p_);
@@ -324,20 +327,18 @@ void host_pipe_destroy(void *p_) {
 // for them (and for the previous user of the slot), and `pd` receives the device-side problem (outputs pointing into
 // the slot). Download half (ba_unstage_host_async): once `stream` has computed, the two results return to the host
 // arrays of `ph` on the download stream.
-extern "C" int ba_stage_host_async(BaPlan *pl, const BaProblem *ph, BaProblem *pd_out, void *stream_) {
-  if (!pl || !ph || !pd_out || !ph->poses || !ph->patches || !ph->intrinsics || !ph->targets || !ph->weights ||
-      !ph->poses_out || !ph->patches_out)
-    return BA_ERR_ARG;
-  if (ph->targets_stride != 0 && ph->targets_stride != 2) return BA_ERR_ARG;
-  cudaStream_t s = (cudaStream_t)stream_;
-  if (int rc = ba::plan_finalize(pl)) return rc;
-  const size_t N = pl->v.N, NM = pl->v.NM, E = (size_t)pl->v.E, m = pl->v.m;
-  const size_t f = sizeof(float);
+namespace {
+struct StageLayout { size_t o_pose, o_pat, o_mono, o_intr, o_tg, o_w, o_lam, o_pout, o_qout, total; };
+StageLayout stage_layout(const BaPlan *pl) {
+  const size_t N = pl->v.N, NM = pl->v.NM, E = (size_t)pl->v.E, m = pl->v.m, f = sizeof(float);
   auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  const size_t o_pose = 0, o_pat = o_pose + up(7 * N * f), o_mono = o_pat + up(3 * NM * f),
-               o_intr = o_mono + up(NM * f), o_tg = o_intr + up(4 * N * f), o_w = o_tg + up(2 * E * f),
-               o_lam = o_w + up(2 * E * f), o_pout = o_lam + up(m * f), o_qout = o_pout + up(7 * N * f),
-               total = o_qout + up(3 * NM * f);
+  StageLayout L;
+  L.o_pose = 0; L.o_pat = L.o_pose + up(7 * N * f); L.o_mono = L.o_pat + up(3 * NM * f); L.o_intr = L.o_mono + up(NM * f);
+  L.o_tg = L.o_intr + up(4 * N * f); L.o_w = L.o_tg + up(2 * E * f); L.o_lam = L.o_w + up(2 * E * f); L.o_pout = L.o_lam + up(m * f);
+  L.o_qout = L.o_pout + up(7 * N * f); L.total = L.o_qout + up(3 * NM * f);
+  return L;
+}
+int host_pipe_get(BaPlan *pl, size_t total, HostPipe **out) {
   HostPipe *hp = static_cast<HostPipe *>(pl->host_pipe);
   if (!hp) {
     hp = new HostPipe();
@@ -355,20 +356,67 @@ extern "C" int ba_stage_host_async(BaPlan *pl, const BaProblem *ph, BaProblem *p
     hp->bytes = total;
   }
   if (hp->bytes < total) return BA_ERR_ARG;            // the plan fixes N, NM, E, m: cannot happen
+  *out = hp;
+  return BA_OK;
+}
+}  // namespace
+
+// Early upload for the NEXT ba_stage_host_async / ba_step_host_async call: the inputs that do not depend on the previous
+// call's results (targets, weights, intrinsics, monodisp, lmbda_vec — whichever pointers of `ph` are non-NULL; poses /
+// patches are ignored) go to that call's staging slot now, on the upload stream, while the previous call still computes.
+// The next call then uploads only what is missing. This is what lets DEPENDENT steps (iteration k+1 starts from the host
+// results of iteration k, main/batrack.py:869-884) hide the 20 MB of per-step observations behind the kernels.
+extern "C" int ba_prefetch_host_async(BaPlan *pl, const BaProblem *ph, void *stream_) {
+  (void)stream_;
+  if (!pl || !ph) return BA_ERR_ARG;
+  if (ph->targets && ph->targets_stride != 0 && ph->targets_stride != 2) return BA_ERR_ARG;
+  if (int rc = ba::plan_finalize(pl)) return rc;
+  const StageLayout L = stage_layout(pl);
+  HostPipe *hp = nullptr;
+  if (int rc = host_pipe_get(pl, L.total, &hp)) return rc;
+  const size_t N = pl->v.N, NM = pl->v.NM, E = (size_t)pl->v.E, m = pl->v.m, f = sizeof(float);
   const int slot = (int)(hp->seq & 1);
   char *d = hp->stage[slot];
-  if (hp->seq >= 2) BA_CUDA(cudaStreamWaitEvent(hp->h2d, hp->computed[slot], 0));   // inputs of call seq-2 consumed
+  if (hp->seq >= 2 && !hp->pre_waited) BA_CUDA(cudaStreamWaitEvent(hp->h2d, hp->computed[slot], 0));   // inputs of call seq-2 consumed
+  hp->pre_waited = true;
+  if (ph->monodisp) { BA_CUDA(cudaMemcpyAsync(d + L.o_mono, ph->monodisp, NM * f, cudaMemcpyHostToDevice, hp->h2d)); hp->pre_mask |= PRE_MONO; }
+  if (ph->intrinsics) { BA_CUDA(cudaMemcpyAsync(d + L.o_intr, ph->intrinsics, 4 * N * f, cudaMemcpyHostToDevice, hp->h2d)); hp->pre_mask |= PRE_INTR; }
+  if (ph->targets) { BA_CUDA(cudaMemcpyAsync(d + L.o_tg, ph->targets, 2 * E * f, cudaMemcpyHostToDevice, hp->h2d)); hp->pre_mask |= PRE_TG; }
+  if (ph->weights) { BA_CUDA(cudaMemcpyAsync(d + L.o_w, ph->weights, 2 * E * f, cudaMemcpyHostToDevice, hp->h2d)); hp->pre_mask |= PRE_W; }
+  if (ph->lmbda_vec) { BA_CUDA(cudaMemcpyAsync(d + L.o_lam, ph->lmbda_vec, m * f, cudaMemcpyHostToDevice, hp->h2d)); hp->pre_mask |= PRE_LAM; }
+  return BA_OK;
+}
+
+extern "C" int ba_stage_host_async(BaPlan *pl, const BaProblem *ph, BaProblem *pd_out, void *stream_) {
+  if (!pl || !ph || !pd_out || !ph->poses || !ph->patches || !ph->intrinsics || !ph->targets || !ph->weights ||
+      !ph->poses_out || !ph->patches_out)
+    return BA_ERR_ARG;
+  if (ph->targets_stride != 0 && ph->targets_stride != 2) return BA_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream_;
+  if (int rc = ba::plan_finalize(pl)) return rc;
+  const size_t N = pl->v.N, NM = pl->v.NM, E = (size_t)pl->v.E, m = pl->v.m;
+  const size_t f = sizeof(float);
+  const StageLayout L = stage_layout(pl);
+  const size_t o_pose = L.o_pose, o_pat = L.o_pat, o_mono = L.o_mono, o_intr = L.o_intr, o_tg = L.o_tg, o_w = L.o_w, o_lam = L.o_lam,
+               o_pout = L.o_pout, o_qout = L.o_qout;
+  HostPipe *hp = nullptr;
+  if (int rc = host_pipe_get(pl, L.total, &hp)) return rc;
+  const int slot = (int)(hp->seq & 1);
+  char *d = hp->stage[slot];
+  if (hp->seq >= 2 && !hp->pre_waited) BA_CUDA(cudaStreamWaitEvent(hp->h2d, hp->computed[slot], 0));   // inputs of call seq-2 consumed
+  const unsigned pre = hp->pre_mask;                   // already on the upload stream (ba_prefetch_host_async)
+  hp->pre_mask = 0; hp->pre_waited = false;
   BaProblem pd = *ph;
-#define H2D(field, off, bytes)                                                                          \
-  do { BA_CUDA(cudaMemcpyAsync(d + (off), ph->field, (bytes), cudaMemcpyHostToDevice, hp->h2d));        \
+#define H2D(field, off, bytes, bit)                                                                     \
+  do { if (!(pre & (bit))) BA_CUDA(cudaMemcpyAsync(d + (off), ph->field, (bytes), cudaMemcpyHostToDevice, hp->h2d)); \
        pd.field = (const float *)(d + (off)); } while (0)
-  H2D(poses, o_pose, 7 * N * f);
-  H2D(patches, o_pat, 3 * NM * f);
-  if (ph->monodisp) H2D(monodisp, o_mono, NM * f);
-  H2D(intrinsics, o_intr, 4 * N * f);
-  H2D(targets, o_tg, 2 * E * f);
-  H2D(weights, o_w, 2 * E * f);
-  if (ph->lmbda_vec) H2D(lmbda_vec, o_lam, m * f);
+  H2D(poses, o_pose, 7 * N * f, 0);
+  H2D(patches, o_pat, 3 * NM * f, 0);
+  if (ph->monodisp) H2D(monodisp, o_mono, NM * f, PRE_MONO);
+  H2D(intrinsics, o_intr, 4 * N * f, PRE_INTR);
+  H2D(targets, o_tg, 2 * E * f, PRE_TG);
+  H2D(weights, o_w, 2 * E * f, PRE_W);
+  if (ph->lmbda_vec) H2D(lmbda_vec, o_lam, m * f, PRE_LAM);
 #undef H2D
   pd.targets_stride = 2;
   BA_CUDA(cudaEventRecord(hp->in_ready[slot], hp->h2d));

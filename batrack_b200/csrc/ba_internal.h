@@ -1,6 +1,7 @@
 // ba_internal.h — plan layout shared by the translation units of libbatrack_ba.so (not installed).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include <atomic>
@@ -240,8 +241,24 @@ inline SolveFeed make_feed(const BaPlan *pl, const int *flags, const int *top_ne
     if (e_ != cudaSuccess) return ba::set_cuda_error(e_, #call);              \
   } while (0)
 
+// NVTX ranges (SURVEY.md §5 tracing): one host-side range per stage of a BA call around its launches ("ba:edge_pass",
+// "ba:schur", ...), and one around a plan build / update; free when no tool is attached.
+namespace ba {
+inline void nvtx_stage(int k) {
+  static const char *const names[BA_N_STAGES] = {"ba:zero", "ba:edge_pass", "ba:track_q", "ba:schur", "ba:solve", "ba:backsub", "ba:pose_retr"};
+  static thread_local bool open = false;
+  if (open) { nvtxRangePop(); open = false; }
+  if (k >= 0 && k < BA_N_STAGES) { nvtxRangePushA(names[k]); open = true; }
+}
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace ba
+
 #define BA_MARK(pl, k, s)                                                     \
   do {                                                                        \
+    ba::nvtx_stage(k);                                                        \
     if ((pl)->timing) { BA_CUDA(cudaEventRecord((pl)->ev[(k)], (s))); (pl)->ev_mask |= 1u << (k); } \
   } while (0)
 

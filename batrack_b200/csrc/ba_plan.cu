@@ -843,6 +843,7 @@ extern "C" int ba_plan_create(const int64_t *ii, const int64_t *jj, const int64_
   if (!out) return BA_ERR_ARG;
   *out = nullptr;
   if (!ii || !jj || !kk || E <= 0 || E >= (int64_t)1 << 31) return BA_ERR_ARG;
+  NvtxRange nvtx_range("ba:plan_create");
   cudaStream_t s = (cudaStream_t)stream_;
   int dev = 0;
   int rc = plan_prologue(N, NM, s, &dev);
@@ -913,6 +914,7 @@ extern "C" int ba_plan_update(BaPlan *pl, const int64_t *ii, const int64_t *jj, 
                               const int32_t *n_edges_dev, void *stream_) {
   if (!pl || !ii || !jj || !kk || n_edges <= 0 || !pl->b.caps.est) return BA_ERR_ARG;
   if (n_edges > pl->b.caps.E) return BA_ERR_CAPACITY;
+  NvtxRange nvtx_range("ba:plan_update");
   cudaStream_t s = (cudaStream_t)stream_;
   PlanBuild &b = pl->b;
   b.valid = 0;

@@ -81,6 +81,30 @@ class HostBA:
                 _capi.check(L.ba_solve_update(self.plan.handle, C.byref(pd), st), "ba_solve_update")
                 _capi.check(L.ba_unstage_host_async(self.plan.handle, C.byref(p), C.byref(pd), st), "ba_unstage_host_async")
 
+    def prefetch(self, patches_monodisp=None, intrinsics=None, targets_2d=None, weights=None, lmbda=None):
+        """Upload the step-independent inputs of the NEXT submit() now (ba_prefetch_host_async): they travel while the
+        previous step still computes, and the next submit() — which must pass the same arrays — uploads only poses and
+        patches. For dependent steps: submit(k); prefetch(inputs of k+1); sync(); submit(k+1, poses / patches of k)."""
+        info = self.plan.info
+        N, NM, E = info.n_poses, info.n_patches, info.n_edges
+        p = _capi.BaProblem()
+        if patches_monodisp is not None:
+            p.monodisp = _host_f32("patches_monodisp", patches_monodisp, (1, NM, 1)).data_ptr()
+        if intrinsics is not None:
+            p.intrinsics = _host_f32("intrinsics", intrinsics, (1, N, 4)).data_ptr()
+        if targets_2d is not None:
+            p.targets = _host_f32("targets_2d", targets_2d, (1, E, 2)).data_ptr()
+            p.targets_stride = 2
+        if weights is not None:
+            p.weights = _host_f32("weights", weights, (1, E, 2)).data_ptr()
+        if isinstance(lmbda, torch.Tensor):
+            lv = _host_f32("lmbda", lmbda.reshape(-1).expand(info.n_tracks).contiguous(), (info.n_tracks,))
+            self._keep.append(lv)
+            p.lmbda_vec = lv.data_ptr()
+        dev = self.plan.device
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().ba_prefetch_host_async(self.plan.handle, C.byref(p), _capi.stream_ptr(dev)), "ba_prefetch_host_async")
+
     def sync(self, block=True):
         """Order the current stream after every submitted step's download; block=True also waits on the host."""
         dev = self.plan.device

@@ -237,6 +237,12 @@ int ba_plan_last_timing(BaPlan *plan, float *ms_out /* host, BA_N_STAGES floats 
 int ba_step_host_async(BaPlan *plan, const BaProblem *prob_host, void *stream);
 int ba_stage_host_async(BaPlan *plan, const BaProblem *prob_host, BaProblem *prob_dev, void *stream);
 int ba_unstage_host_async(BaPlan *plan, const BaProblem *prob_host, const BaProblem *prob_dev, void *stream);
+/* Early upload for the NEXT ba_step_host_async / ba_stage_host_async call: whichever of targets, weights, intrinsics,
+ * monodisp, lmbda_vec are non-NULL in `problem_host` (inputs that do not depend on the previous call's results; poses /
+ * patches are ignored) go to that call's staging slot on the upload stream now, while the previous call still computes;
+ * the next call uploads only the rest. Lets DEPENDENT steps (BATRACK.update feeds iteration k+1 with iteration k's poses
+ * and patches, main/batrack.py:869-884) hide the per-step observations behind the kernels. */
+int ba_prefetch_host_async(BaPlan *plan, const BaProblem *problem_host, void *stream);
 int ba_host_sync(BaPlan *plan, void *stream, int block);
 int ba_step_host(BaPlan *plan, const BaProblem *prob_host, void *stream);
 

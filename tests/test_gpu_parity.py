@@ -469,6 +469,22 @@ def test_host_buffer_pipeline_equals_device_call():
         # S / y are summed with fp64 atomics in a run-dependent order: equal to rounding, not bitwise
         assert rel_err(op.numpy(), G.data.cpu().numpy()) < 1e-6
         assert rel_err(oq.numpy(), p.cpu().numpy()) < 1e-6
+    # dependent steps with the early upload of the step-independent inputs (ba_prefetch_host_async): step k+1 starts from
+    # the host results of step k; the chain equals the same chain on device tensors
+    chain = [(torch.empty(1, N, 7).pin_memory(), torch.empty(1, NM, 3, 1, 1).pin_memory()) for _ in range(3)]
+    cur = (host["poses"], host["patches"])
+    for k in range(3):
+        hba.submit(cur[0], cur[1], host["patches_monodisp"], host["intrinsics"], host["targets_2d"], ws[k], ps.lmbda, ps.bounds,
+                   chain[k][0], chain[k][1], ep=ps.ep, fixedp=ps.fixedp, structure_only=False, loss=ps.loss, alpha=ps.alpha)
+        if k + 1 < 3:
+            hba.prefetch(host["patches_monodisp"], host["intrinsics"], host["targets_2d"], ws[k + 1])
+        hba.sync()
+        cur = chain[k]
+    G, p = SE3(t["poses"]), t["patches"]
+    for k in range(3):
+        G, p = BA_rgbd_droid(G, p, t["patches_monodisp"], t["intrinsics"], t["targets_2d"], None, ws[k].cuda(), ps.lmbda, t["ii"], t["jj"],
+                             t["kk"], ps.bounds, ep=ps.ep, fixedp=ps.fixedp, structure_only=False, loss=ps.loss, alpha=ps.alpha, plan=plan)
+        assert rel_err(chain[k][0].numpy(), G.data.cpu().numpy()) < 1e-5 and rel_err(chain[k][1].numpy(), p.cpu().numpy()) < 1e-5
     with pytest.raises(RuntimeError):
         hba.submit(t["poses"], host["patches"], host["patches_monodisp"], host["intrinsics"], host["targets_2d"], ws[0],
                    ps.lmbda, ps.bounds, *outs[0])
