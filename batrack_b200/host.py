@@ -40,6 +40,8 @@ class HostBA:
         ba_unstage_host_async."""
         if loss not in _capi.LOSS_IDS:
             raise NotImplementedError(loss)
+        if getattr(self.plan, "_stale", False):
+            self.plan.finalize()                          # CapacityPlan.update(): read its counts now
         info = self.plan.info
         N, NM, E = info.n_poses, info.n_patches, info.n_edges
         p = _capi.BaProblem()
