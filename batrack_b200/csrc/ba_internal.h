@@ -58,6 +58,7 @@ struct PlanView {
   const ChunkDesc *cdesc;  // [n_chunks]
   // lane-per-track edge pass (regular groups): CTA units of <= 32 * (kEdge2Warps / e2_kp) tracks
   int e2_kp;               // position splits per track slice (1, 2, 4 or 8)
+  int e2_tpl;              // tracks per lane (1, or 2 on large graphs): CTA units of <= 32 * e2_tpl * (kEdge2Warps / e2_kp) tracks
   const int *x_t0, *x_grp; // [n_xchunks+1], [n_xchunks]
   int n_xchunks;
   const int *g_reg;        // [G] 1 = regular group (one source slot; no target slot fed more than kMaxSlotRun times)
@@ -113,7 +114,7 @@ struct BaOptions {
 // capacity plan (ba_plan_create_capacity) is sized once for the largest graph the caller will ever hand to ba_plan_update.
 struct BaCaps { int64_t E; int m, G, pat, units[4]; int64_t est; };
 // host-chosen overrides of the derived unit lengths (environment, experiments): -1 = derive on device
-struct BaTuning { int tc, tu, kp, to, gend; };
+struct BaTuning { int tc, tu, kp, to, gend, tpl; };
 // Everything the device-side build of a plan writes (ba_plan.cu): plan arrays (the PlanView points into them), build
 // scratch, the shape block and its pinned host copy.
 struct PlanBuild {

@@ -355,24 +355,29 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
 //     fp64 atomics, with Bii / vi pre-summed over the positions (they all hit the same pose block).
 // =================================================================================================
 constexpr int kE2PosBlock = 32;                 // positions per block (constants / per-position sums staged per block)
-constexpr int kE2Slice = 4;                     // positions per cp.async slice
+// TPL = tracks per lane. 1: lane <-> track. 2 (large graphs): a lane walks tracks t and t + 32 together — the per-position
+// constants, the control flow and the 27-value transpose reduction are shared by two edges, and the two independent edge
+// computations give the in-order warp instruction-level parallelism (the kernel is bound by instruction issue, not HBM).
+constexpr int e2_slice(int tpl) { return tpl == 2 ? 2 : 4; }       // positions per cp.async slice
 constexpr int kE2RedStride = 36;                // floats per row of the transpose buffer (conflict-free both ways)
 constexpr int kE2AccStride = 28;
-constexpr int kE2ArrF2 = 32 * (kE2Slice + 1);                       // float2 per staged array: [track][slice + 1]
-constexpr int kE2WarpScratch = kAccComps * kE2RedStride + 2 * 2 * 2 * kE2ArrF2;   // floats: transpose buffer + 2 stages x (targets, weights)
+constexpr int e2_arr_f2(int tpl) { return 32 * tpl * (e2_slice(tpl) + 1); }            // float2 per staged array: [track][slice + 1]
+constexpr int e2_warp_scratch(int tpl) { return kAccComps * kE2RedStride + 2 * 2 * 2 * e2_arr_f2(tpl); }   // floats: transpose buffer + 2 stages x (targets, weights)
+constexpr int kE2WarpScratch = e2_warp_scratch(1);                  // the smaller of the two: what the flush scratch may count on
 constexpr int kE2Threads = 32 * kEdge2Warps;
 constexpr int kE2FlushPos = (kEdge2Warps * kE2WarpScratch * 4) / ((kAccComps + 36 + kFlushOuts) * 8) < kE2PosBlock
                                 ? (kEdge2Warps * kE2WarpScratch * 4) / ((kAccComps + 36 + kFlushOuts) * 8) : kE2PosBlock;
 // dynamic shared memory: per warp scratch, per track slice (KT = kEdge2Warps / KP) the per-position sums, constants
-static size_t edge2_smem_bytes(int kp) {
-  return (size_t)(kEdge2Warps * kE2WarpScratch + (kEdge2Warps / kp) * kE2PosBlock * kE2AccStride +
+static size_t edge2_smem_bytes(int kp, int tpl) {
+  return (size_t)(kEdge2Warps * e2_warp_scratch(tpl) + (kEdge2Warps / kp) * kE2PosBlock * kE2AccStride +
                   kE2PosBlock * kPosFloats + 5 * kE2PosBlock + 8) * sizeof(float);
 }
 static_assert(kE2FlushPos >= 1, "flush scratch too small");
-static_assert(kEdge2Warps * 8 * 32 <= kEdge2Warps * kE2WarpScratch, "per-track partials alias the scratch");
+static_assert(kEdge2Warps * 8 * 64 <= kEdge2Warps * kE2WarpScratch, "per-track partials alias the scratch");
 
-template <bool STRUCT_ONLY>
-__global__ void __launch_bounds__(kE2Threads, 3) k_edge_pass_v2(PlanView pv, CallView cv) {
+template <bool STRUCT_ONLY, int TPL>
+__global__ void __launch_bounds__(kE2Threads, TPL == 2 ? 2 : 3) k_edge_pass_v2(PlanView pv, CallView cv) {
+  constexpr int kE2Slice = e2_slice(TPL), kE2ArrF2 = e2_arr_f2(TPL), kWarpScratch = e2_warp_scratch(TPL);
   extern __shared__ __align__(16) float dyn_smem[];
   const int tau = threadIdx.x, lane = tau & 31, warp = tau >> 5;
   const int xc = blockIdx.x;
@@ -391,9 +396,9 @@ __global__ void __launch_bounds__(kE2Threads, 3) k_edge_pass_v2(PlanView pv, Cal
   const bool fi = pose_free(slot_pose[li], cv);                    // ba.py:33-39 masks
 
   float *scratch = dyn_smem;                                       // [warps][kE2WarpScratch]; fp64 flush scratch afterwards
-  float *red = scratch + warp * kE2WarpScratch;                    // [27][36]
+  float *red = scratch + warp * kWarpScratch;                      // [27][36]
   float2 *stage = reinterpret_cast<float2 *>(red + kAccComps * kE2RedStride);   // [2][2][32][slice + 1]
-  float *sacc_all = scratch + kEdge2Warps * kE2WarpScratch;        // [track slice][32][28]
+  float *sacc_all = scratch + kEdge2Warps * kWarpScratch;          // [track slice][32][28]
   float *sacc = sacc_all + ks * (kE2PosBlock * kE2AccStride);
   float *sconst = sacc_all + (kEdge2Warps / KP) * (kE2PosBlock * kE2AccStride); // [32][20]
   int *slj = reinterpret_cast<int *>(sconst + kE2PosBlock * kPosFloats);        // [32 + 1] target slot of the position (+ look-ahead)
@@ -403,18 +408,26 @@ __global__ void __launch_bounds__(kE2Threads, 3) k_edge_pass_v2(PlanView pv, Cal
   int *hlist = spj + kE2PosBlock;                                               // [32] block positions that start a slot run
   int *s_ctl = hlist + kE2PosBlock;                                             // [0] positions in this block, [1] run heads
 
-  const int tw0 = t0 + 32 * ks;                                    // first track of this warp's slice
-  const int t = tw0 + lane;
-  const bool have = t < t1;
+  const int tw0 = t0 + 32 * TPL * ks;                              // first track of this warp's slice (lane: tracks tw0 + lane [+ 32])
   const bool warp_has = tw0 < t1;
-  float ppx = 0.0f, ppy = 0.0f, ppd = 1.0f;
-  if (have) {
-    const float *pp = cv.patches + 3 * (size_t)__ldg(pv.kx + t);
-    ppx = __ldg(pp); ppy = __ldg(pp + 1); ppd = __ldg(pp + 2);
+  int t[TPL];
+  bool have[TPL];
+  float ppx[TPL], ppy[TPL], ppd[TPL], C[TPL], w[TPL], Eis[TPL][6], Ejs[TPL][6];
+#pragma unroll
+  for (int u = 0; u < TPL; ++u) {
+    t[u] = tw0 + 32 * u + lane;
+    have[u] = t[u] < t1;
+    ppx[u] = 0.0f; ppy[u] = 0.0f; ppd[u] = 1.0f;
+    if (have[u]) {
+      const float *pp = cv.patches + 3 * (size_t)__ldg(pv.kx + t[u]);
+      ppx[u] = __ldg(pp); ppy[u] = __ldg(pp + 1); ppd[u] = __ldg(pp + 2);
+    }
+    C[u] = 0.0f; w[u] = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { Eis[u][a] = 0.0f; Ejs[u][a] = 0.0f; }
   }
-  float C = 0.0f, w = 0.0f, Eis[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Ejs[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int hd = 0;
-  const int nS = min(kEdge2Warps / KP, (t1 - t0 + 31) >> 5);       // track slices of this CTA that own tracks
+  const int nS = min(kEdge2Warps / KP, (t1 - t0 + 32 * TPL - 1) / (32 * TPL));   // track slices of this CTA that own tracks
 
   // The walk follows pat_ps: positions ordered by target slot, so that the positions feeding one E slot (a SLAM
   // graph observes a (patch, frame) pair several times) are consecutive; blocks of <= 32 positions and the KP
@@ -465,7 +478,7 @@ __global__ void __launch_bounds__(kE2Threads, 3) k_edge_pass_v2(PlanView pv, Cal
         const int pl = pw0 + kE2Slice * sl + pp;
         if (pl < pw1) {
 #pragma unroll
-          for (int k = 0; k < kE2Slice; ++k) {
+          for (int k = 0; k < TPL * kE2Slice; ++k) {
             const int tk = lane / kE2Slice + (32 / kE2Slice) * k, tt = tw0 + tk;
             if (tt < t1) {
               const int q = ebase + (tt - gt0) * d + spp[pl];
@@ -490,8 +503,6 @@ __global__ void __launch_bounds__(kE2Threads, 3) k_edge_pass_v2(PlanView pv, Cal
         const int npp = min(kE2Slice, pw1 - pw0 - kE2Slice * sl);
         for (int pp = 0; pp < npp; ++pp) {
           const int pl = pw0 + kE2Slice * sl + pp;                 // position within the block (warp-uniform)
-          float2 tg = bt[pp], wg = bt[kE2ArrF2 + pp];
-          if (!have) { tg = make_float2(0.f, 0.f); wg = make_float2(0.f, 0.f); }
           const float4 *cs = reinterpret_cast<const float4 *>(sconst + pl * kPosFloats);
           const float4 c0 = cs[0], c1 = cs[1], c2 = cs[2], c3 = cs[3], c4 = cs[4];
           PairConst pc;
@@ -500,55 +511,85 @@ __global__ void __launch_bounds__(kE2Threads, 3) k_edge_pass_v2(PlanView pv, Cal
           pc.R[8] = c2.x; pc.t = {c2.y, c2.z, c2.w};
           pc.cxi = c3.z; pc.cyi = c3.w; pc.fxj = c4.x; pc.fyj = c4.y; pc.cxj = c4.z; pc.cyj = c4.w;
           pc.fxi = 0.f; pc.fyi = 0.f;                              // unused: the inverses are passed separately
-          EdgeTerms et;
-          edge_terms(pc, c3.x, c3.y, ppx, ppy, ppd, tg.x, tg.y, wg.x, wg.y, cv.bounds, cv.loss, et);
-          const float wz0 = et.w0 * et.Jz0, wz1 = et.w1 * et.Jz1;  // (w Jz)^T, ba.py:255
-          C += wz0 * et.Jz0 + wz1 * et.Jz1;                        // ba.py:287
-          w += wz0 * et.r0 + wz1 * et.r1;                          // ba.py:292
+          EdgeTerms et[TPL];
+#pragma unroll
+          for (int u = 0; u < TPL; ++u) {
+            float2 tg = bt[32 * u * (kE2Slice + 1) + pp], wg = bt[kE2ArrF2 + 32 * u * (kE2Slice + 1) + pp];
+            if (!have[u]) { tg = make_float2(0.f, 0.f); wg = make_float2(0.f, 0.f); }
+            edge_terms(pc, c3.x, c3.y, ppx[u], ppy[u], ppd[u], tg.x, tg.y, wg.x, wg.y, cv.bounds, cv.loss, et[u]);
+            const float wz0 = et[u].w0 * et[u].Jz0, wz1 = et[u].w1 * et[u].Jz1;  // (w Jz)^T, ba.py:255
+            C[u] += wz0 * et[u].Jz0 + wz1 * et[u].Jz1;             // ba.py:287
+            w[u] += wz0 * et[u].r0 + wz1 * et[u].r1;               // ba.py:292
+          }
           if (!STRUCT_ONLY) {
             // Jj0[1] and Jj1[0] are structural zeros (projective_ops.py:83-95): entries that involve component 0 /
-            // component 1 have one term only, Bjj(1,0) vanishes (adding the exact zero the reference adds)
-            float Ej[6], Ei[6];
+            // component 1 have one term only, Bjj(1,0) vanishes (adding the exact zero the reference adds). The transpose
+            // buffer gets the lane's sum over its TPL tracks.
+            float Ej[TPL][6];
             {
-              const float wa00 = et.w0 * et.Jj0[0], wa11 = et.w1 * et.Jj1[1];   // (w Jj)^T, ba.py:254
-              Ej[0] = wa00 * et.Jz0; Ej[1] = wa11 * et.Jz1;                     // Ejk, ba.py:263
-              red[21 * kE2RedStride + lane] = wa00 * et.r0;                     // vj, ba.py:266
-              red[22 * kE2RedStride + lane] = wa11 * et.r1;
-              red[tri(0, 0) * kE2RedStride + lane] = wa00 * et.Jj0[0];          // Bjj, ba.py:260
+              float s21 = 0.f, s22 = 0.f, s00 = 0.f, s11 = 0.f;
+#pragma unroll
+              for (int u = 0; u < TPL; ++u) {
+                const float wa00 = et[u].w0 * et[u].Jj0[0], wa11 = et[u].w1 * et[u].Jj1[1];   // (w Jj)^T, ba.py:254
+                Ej[u][0] = wa00 * et[u].Jz0; Ej[u][1] = wa11 * et[u].Jz1;                     // Ejk, ba.py:263
+                s21 += wa00 * et[u].r0; s22 += wa11 * et[u].r1;                               // vj, ba.py:266
+                s00 += wa00 * et[u].Jj0[0]; s11 += wa11 * et[u].Jj1[1];                       // Bjj, ba.py:260
+              }
+              red[21 * kE2RedStride + lane] = s21;
+              red[22 * kE2RedStride + lane] = s22;
+              red[tri(0, 0) * kE2RedStride + lane] = s00;
               red[tri(1, 0) * kE2RedStride + lane] = 0.0f;
-              red[tri(1, 1) * kE2RedStride + lane] = wa11 * et.Jj1[1];
+              red[tri(1, 1) * kE2RedStride + lane] = s11;
 #pragma unroll
               for (int a = 2; a < 6; ++a) {
-                const float wa0 = et.w0 * et.Jj0[a], wa1 = et.w1 * et.Jj1[a];
-                Ej[a] = fmaf(wa1, et.Jz1, wa0 * et.Jz0);
-                red[(21 + a) * kE2RedStride + lane] = fmaf(wa1, et.r1, wa0 * et.r0);
-                red[tri(a, 0) * kE2RedStride + lane] = wa0 * et.Jj0[0];
-                red[tri(a, 1) * kE2RedStride + lane] = wa1 * et.Jj1[1];
+                float wa0[TPL], wa1[TPL];
+                float sv = 0.f, sa0 = 0.f, sa1 = 0.f;
 #pragma unroll
-                for (int b = 2; b <= a; ++b) red[tri(a, b) * kE2RedStride + lane] = fmaf(wa1, et.Jj1[b], wa0 * et.Jj0[b]);
+                for (int u = 0; u < TPL; ++u) {
+                  wa0[u] = et[u].w0 * et[u].Jj0[a]; wa1[u] = et[u].w1 * et[u].Jj1[a];
+                  Ej[u][a] = fmaf(wa1[u], et[u].Jz1, wa0[u] * et[u].Jz0);
+                  sv += fmaf(wa1[u], et[u].r1, wa0[u] * et[u].r0);
+                  sa0 += wa0[u] * et[u].Jj0[0];
+                  sa1 += wa1[u] * et[u].Jj1[1];
+                }
+                red[(21 + a) * kE2RedStride + lane] = sv;
+                red[tri(a, 0) * kE2RedStride + lane] = sa0;
+                red[tri(a, 1) * kE2RedStride + lane] = sa1;
+#pragma unroll
+                for (int b = 2; b <= a; ++b) {
+                  float sb = 0.f;
+#pragma unroll
+                  for (int u = 0; u < TPL; ++u) sb += fmaf(wa1[u], et[u].Jj1[b], wa0[u] * et[u].Jj0[b]);
+                  red[tri(a, b) * kE2RedStride + lane] = sb;
+                }
               }
             }
-            adjT_apply(pc.R, pc.t, Ej, Ei);                                     // Eik = -A Ejk, ba.py:262
-#pragma unroll
-            for (int a = 0; a < 6; ++a) Eis[a] -= Ei[a];
             const int lj = slj[pl];
             const bool head = pl == pw0 || lj != slj[pl - 1];                   // first position of a slot run
-            if (lj == li) {                                                     // self edge: its j side feeds the source slot too
+            const bool run_end = pl + 1 == pw1 || slj[pl + 1] != lj;            // last position of the run: the one store
 #pragma unroll
-              for (int a = 0; a < 6; ++a) Eis[a] += Ej[a];
-            } else {
-              if (head) {
+            for (int u = 0; u < TPL; ++u) {
+              float Ei[6];
+              adjT_apply(pc.R, pc.t, Ej[u], Ei);                                // Eik = -A Ejk, ba.py:262
 #pragma unroll
-                for (int a = 0; a < 6; ++a) Ejs[a] = Ej[a];
+              for (int a = 0; a < 6; ++a) Eis[u][a] -= Ei[a];
+              if (lj == li) {                                                   // self edge: its j side feeds the source slot too
+#pragma unroll
+                for (int a = 0; a < 6; ++a) Eis[u][a] += Ej[u][a];
               } else {
+                if (head) {
 #pragma unroll
-                for (int a = 0; a < 6; ++a) Ejs[a] += Ej[a];
-              }
-              if (have && (pl + 1 == pw1 || slj[pl + 1] != lj)) {               // last position of the run: the one store
-                const bool fj = sfj[pl] != 0;
-                float *col = Eb + (size_t)(6 * lj) * Ts + (t - gt0);
+                  for (int a = 0; a < 6; ++a) Ejs[u][a] = Ej[u][a];
+                } else {
 #pragma unroll
-                for (int a = 0; a < 6; ++a) col[(size_t)a * Ts] = fj ? Ejs[a] : 0.0f;
+                  for (int a = 0; a < 6; ++a) Ejs[u][a] += Ej[u][a];
+                }
+                if (have[u] && run_end) {
+                  const bool fj = sfj[pl] != 0;
+                  float *col = Eb + (size_t)(6 * lj) * Ts + (t[u] - gt0);
+#pragma unroll
+                  for (int a = 0; a < 6; ++a) col[(size_t)a * Ts] = fj ? Ejs[u][a] : 0.0f;
+                }
               }
             }
             if (head) hd = pl;
@@ -659,38 +700,49 @@ __global__ void __launch_bounds__(kE2Threads, 3) k_edge_pass_v2(PlanView pv, Cal
   // ---- per track: the KP partial sums meet in shared memory (fixed order), then Q, w and the source slot's E ----
   if (KP > 1) {
     __syncthreads();
-    float *tp = scratch + warp * (8 * 32);                         // [8][32] per warp
-    tp[lane] = C; tp[32 + lane] = w;
+    float *tp = scratch + warp * (8 * 32 * TPL);                   // [TPL][8][32] per warp
 #pragma unroll
-    for (int a = 0; a < 6; ++a) tp[(2 + a) * 32 + lane] = Eis[a];
+    for (int u = 0; u < TPL; ++u) {
+      float *tu = tp + u * (8 * 32);
+      tu[lane] = C[u]; tu[32 + lane] = w[u];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) tu[(2 + a) * 32 + lane] = Eis[u][a];
+    }
     __syncthreads();
     if (sp == 0) {
       for (int k = 1; k < KP; ++k) {
-        const float *o = scratch + (warp + k) * (8 * 32);
-        C += o[lane]; w += o[32 + lane];
 #pragma unroll
-        for (int a = 0; a < 6; ++a) Eis[a] += o[(2 + a) * 32 + lane];
+        for (int u = 0; u < TPL; ++u) {
+          const float *o = scratch + (warp + k) * (8 * 32 * TPL) + u * (8 * 32);
+          C[u] += o[lane]; w[u] += o[32 + lane];
+#pragma unroll
+          for (int a = 0; a < 6; ++a) Eis[u][a] += o[(2 + a) * 32 + lane];
+        }
       }
     }
   }
-  if (have && sp == 0) {
-    if (!STRUCT_ONLY) {
-      float *col = Eb + (size_t)(6 * li) * Ts + (t - gt0);
 #pragma unroll
-      for (int a = 0; a < 6; ++a) col[(size_t)a * Ts] = fi ? Eis[a] : 0.0f;
+  for (int u = 0; u < TPL; ++u) {
+    if (have[u] && sp == 0) {
+      if (!STRUCT_ONLY) {
+        float *col = Eb + (size_t)(6 * li) * Ts + (t[u] - gt0);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) col[(size_t)a * Ts] = fi ? Eis[u][a] : 0.0f;
+      }
+      // damped inverse Q and prior-adjusted w (ba.py:296-311; BA: :184)
+      const float lam = cv.lmbda_vec ? cv.lmbda_vec[t[u]] : cv.lmbda;
+      float Cc = C[u], ww = w[u];
+      if (cv.monodisp) {
+        const float md = __ldg(cv.monodisp + (size_t)__ldg(pv.kx + t[u]));
+        const float mk = md > 1e-2f ? 1.0f : 0.0f;
+        Cc = Cc + mk * cv.alpha;
+        Cc = Cc + lam;
+        ww = ww - mk * cv.alpha * (ppd[u] - md);
+      } else {
+        Cc = Cc + lam;
+      }
+      cv.Qw[t[u]] = make_float2(1.0f / Cc, ww);
     }
-    // damped inverse Q and prior-adjusted w (ba.py:296-311; BA: :184)
-    const float lam = cv.lmbda_vec ? cv.lmbda_vec[t] : cv.lmbda;
-    if (cv.monodisp) {
-      const float md = __ldg(cv.monodisp + (size_t)__ldg(pv.kx + t));
-      const float mk = md > 1e-2f ? 1.0f : 0.0f;
-      C = C + mk * cv.alpha;
-      C = C + lam;
-      w = w - mk * cv.alpha * (ppd - md);
-    } else {
-      C = C + lam;
-    }
-    cv.Qw[t] = make_float2(1.0f / C, w);
   }
 }
 
@@ -1340,8 +1392,10 @@ namespace ba {
 int kernels_prepare_device() {
   BA_CUDA(cudaFuncSetAttribute(k_edge_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
   BA_CUDA(cudaFuncSetAttribute(k_edge_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
-  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1)));
-  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1)));
+  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1, 1)));
+  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1, 1)));
+  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1, 2)));
+  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1, 2)));
   BA_CUDA(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BA_CUDA(cudaFuncSetAttribute(k_solve_window, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
   BA_CUDA(cudaFuncSetAttribute(k_solve_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
@@ -1371,7 +1425,11 @@ static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int str
   }
   if (so) {
     BA_MARK(pl, BA_STAGE_EDGE, s);
-    if (any_regular) { k_edge_pass_v2<true><<<pv.n_xchunks, kE2Threads, edge2_smem_bytes(pv.e2_kp), s>>>(pv, cv); BA_LAUNCH_CHECK(); }
+    if (any_regular) {
+      if (pv.e2_tpl == 2) k_edge_pass_v2<true, 2><<<pv.n_xchunks, kE2Threads, edge2_smem_bytes(pv.e2_kp, 2), s>>>(pv, cv);
+      else k_edge_pass_v2<true, 1><<<pv.n_xchunks, kE2Threads, edge2_smem_bytes(pv.e2_kp, 1), s>>>(pv, cv);
+      BA_LAUNCH_CHECK();
+    }
     if (any_irregular) { k_edge_pass<true><<<pv.n_chunks, kEdgeThreads, kEdgeSmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
     if (has_long) { k_edge_pass_long<true><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
   } else {
@@ -1384,7 +1442,11 @@ static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int str
       BA_CUDA(cudaStreamWaitEvent(pl->solve_stream, pl->ev_step_begin, 0));
     }
     BA_MARK(pl, BA_STAGE_EDGE, s);
-    if (any_regular) { k_edge_pass_v2<false><<<pv.n_xchunks, kE2Threads, edge2_smem_bytes(pv.e2_kp), s>>>(pv, cv); BA_LAUNCH_CHECK(); }
+    if (any_regular) {
+      if (pv.e2_tpl == 2) k_edge_pass_v2<false, 2><<<pv.n_xchunks, kE2Threads, edge2_smem_bytes(pv.e2_kp, 2), s>>>(pv, cv);
+      else k_edge_pass_v2<false, 1><<<pv.n_xchunks, kE2Threads, edge2_smem_bytes(pv.e2_kp, 1), s>>>(pv, cv);
+      BA_LAUNCH_CHECK();
+    }
     if (any_irregular) { k_edge_pass<false><<<pv.n_chunks, kEdgeThreads, kEdgeSmemBytes, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
     if (has_long) { k_edge_pass_long<false><<<pv.n_chunks, kEdgeThreads, 0, s>>>(pv, cv); BA_LAUNCH_CHECK(); }
   }

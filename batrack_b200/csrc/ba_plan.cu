@@ -41,7 +41,7 @@ int set_cuda_error(cudaError_t e, const char *what) {
 // kernel needs the host to read a count back) and copied to the host once, at the end.
 enum { META_ERR = 0, META_MAXPOSE, META_NOTIDENT, META_DMAX, META_WMAX, META_SPAN, META_NIRREG, META_DMAX_IRREG, META_MINUNIT, META_MINOUNIT,
        SH_E, SH_M, SH_G, SH_CNT0, SH_CNT1, SH_CNT2, SH_CNT3, SH_PAT, SH_OVERFLOW, SH_LEN0, SH_LEN1, SH_LEN2, SH_LEN3, SH_KP, SH_OMAX,
-       SH_ESIZE_LO, SH_ESIZE_HI, SH_GEND, META_COUNT = 32 };
+       SH_ESIZE_LO, SH_ESIZE_HI, SH_GEND, SH_TPL, META_COUNT = 32 };
 
 __global__ void k_shape_init(int *__restrict__ sh, int E_host, const int *__restrict__ E_dev) {
   const int t = threadIdx.x;
@@ -158,12 +158,16 @@ __global__ void k_derive(const int *__restrict__ g_pat, int cap_G, int cap_pat, 
   // per edge (fewest flushes; measured at 256 KF / 64k tracks: 44 us vs 54 / 60 us with 2 / 4 splits); graphs with few
   // tracks split the positions until the machine sees ~12 warps per SM (25-frame window, 5200 tracks x <= 72 edges:
   // 70 / 53 / 39 us with 2 / 4 / 8 splits)
+  // Two tracks per lane when there are enough tracks to keep every scheduler busy that way (the large graphs, where the
+  // kernel is bound by instruction issue): constants, control flow and the transpose reduction are shared by two edges.
+  int tpl = cdiv(m, 64) >= 4 * sms ? 2 : 1;
+  if (tun.tpl > 0) tpl = tun.tpl;
   int kp = 1;
-  while (kp < kEdge2Warps && (long long)cdiv(m, 32) * kp < 12 * sms && cdiv(dmax, kp) > 2) kp *= 2;
+  while (kp < kEdge2Warps && (long long)cdiv(m, 32 * tpl) * kp < 12 * sms && cdiv(dmax, kp) > 2) kp *= 2;
   if (tun.kp > 0) kp = tun.kp;
   const int to = tun.to > 0 ? tun.to : 64;                   // Schur units of the streaming hand-over to the solver
-  meta[SH_LEN0] = tc; meta[SH_LEN1] = tu; meta[SH_LEN2] = 32 * (kEdge2Warps / kp); meta[SH_LEN3] = to;
-  meta[SH_KP] = kp;
+  meta[SH_LEN0] = tc; meta[SH_LEN1] = tu; meta[SH_LEN2] = 32 * tpl * (kEdge2Warps / kp); meta[SH_LEN3] = to;
+  meta[SH_KP] = kp; meta[SH_TPL] = tpl;
   const int gend = tun.gend >= 0 ? min(tun.gend, G) : G;     // optionally large units in the middle of the pose range
   meta[SH_GEND] = gend;
   meta[SH_OMAX] = gend < G - gend ? max(to, 256) : to;
@@ -614,7 +618,8 @@ using namespace ba;
 namespace ba {
 
 static BaTuning tuning_from_env() {
-  BaTuning t = {-1, -1, -1, -1, -1};
+  BaTuning t = {-1, -1, -1, -1, -1, -1};
+  if (const char *e = getenv("BA_EDGE2_TPL")) { int v2 = atoi(e); if (v2 == 1 || v2 == 2) t.tpl = v2; }
   if (const char *e = getenv("BA_EDGE_TC")) t.tc = std::max(1, atoi(e));
   if (const char *e = getenv("BA_SCHUR_TU")) t.tu = std::max(1, atoi(e));
   if (const char *e = getenv("BA_EDGE2_KP")) { int v2 = atoi(e); if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8) t.kp = v2; }
@@ -771,7 +776,7 @@ int plan_finalize(BaPlan *pl) {
   v.E = h[SH_E]; v.m = h[SH_M]; v.G = h[SH_G];
   v.n_chunks = h[SH_CNT0]; v.n_units = h[SH_CNT1]; v.n_xchunks = h[SH_CNT2]; v.n_ounits = h[SH_CNT3];
   v.perm_identity = h[META_NOTIDENT] ? 0 : 1;
-  v.dmax = h[META_DMAX]; v.e2_kp = h[SH_KP];
+  v.dmax = h[META_DMAX]; v.e2_kp = h[SH_KP]; v.e2_tpl = h[SH_TPL];
   v.n_irregular = h[META_NIRREG]; v.dmax_irregular = h[META_DMAX_IRREG];
   BaPlanInfo &in = pl->info;
   in.n_edges = v.E; in.n_poses = v.N; in.n_patches = v.NM; in.n_total = h[META_MAXPOSE] + 1;
