@@ -81,7 +81,7 @@ def run_reference(args, rank):
     not vendored) and /root/reference does not exist on the GPU box."""
     if rank != 0:
         return
-    from batrack_b200 import synth
+    import synth
     from oracle import ba_oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -148,7 +148,7 @@ def davis_like_update(dev, reps=20):
     bookkeeping replayed with configs/davis_demo.yaml parameters (400 patches/frame, S_slam 12, kf_stride 2,
     OPTIMIZATION_WINDOW 15) on synthetic tracks; one BATRACK.update() = ITER(4) x {pose call, structure-only call}
     (main/batrack.py:869-875). Reported: milliseconds per update(), device time, inputs resident."""
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.lietorch import SE3
     ps, w_all = synth.make_slam_problem(n_frames=25, patches_per_frame=400, seed=7, buffer_size=64)
@@ -273,7 +273,8 @@ def main():
                                                                "cfg5: synthetic 1024-KF / 262144-track / 4980736-edge")
 
     import torch.distributed as dist
-    from batrack_b200 import _capi, synth
+    from batrack_b200 import _capi
+    import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.host import HostBA
     from batrack_b200.lietorch import SE3

@@ -31,7 +31,7 @@ import backend.projective_ops as pops               # noqa: E402
 from backend.lietorch import SE3                    # noqa: E402
 import lietorch_backends as shim                    # noqa: E402
 
-from batrack_b200 import synth                      # noqa: E402
+import synth                      # noqa: E402
 
 
 def run_ref(prob, weights_seq, structure_seq, dtype, variant="rgbd", lmbda=None, loss=None):

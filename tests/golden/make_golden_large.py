@@ -17,7 +17,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from batrack_b200 import synth          # noqa: E402
+import synth          # noqa: E402
 from oracle import ba_oracle            # noqa: E402
 
 for name, iters, out in (("cfg3", 10, "cfg3_x10_sparse64.npz"), ("cfg5", 2, "cfg5_x2_sparse64.npz")):

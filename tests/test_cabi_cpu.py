@@ -47,7 +47,7 @@ def test_struct_layout_matches_header():
 
 def test_product_path_refuses_cpu_tensors():
     """No CPU fallback: the operator raises on host tensors instead of silently computing there."""
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.lietorch import SE3
     prob = synth.make_config("tiny")
@@ -70,7 +70,7 @@ def test_product_does_not_import_oracle():
 
 
 def test_synth_shards_partition_the_graph():
-    from batrack_b200 import synth
+    import synth
     import numpy as np
     full = synth.make_config("cfg1")
     parts = [synth.make_config("cfg1", kf_lo=lo, kf_hi=hi) for lo, hi in ((0, 3), (3, 8))]

@@ -29,7 +29,7 @@ def slam_graph_sequence(n_frames, M, s_slam=12, kf_stride=2, removal_window=20):
 
 def _random_problem(rng, N, NM, ii, jj, kk, dev):
     """Inputs of one BA call on the graph (geometry does not matter for a plan-vs-plan comparison)."""
-    from batrack_b200 import synth
+    import synth
     gt = synth._exp(np.cumsum(rng.normal(size=(N, 6)) * np.array([0.02] * 3 + [0.004] * 3), axis=0))
     intr = np.tile(np.array([800.0, 800.0, 480.0, 270.0]), (N, 1))
     xyd = np.stack([rng.uniform(30, 930, NM), rng.uniform(30, 510, NM), rng.uniform(0.2, 1.2, NM)], 1)

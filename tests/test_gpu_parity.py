@@ -65,7 +65,7 @@ def test_stagewise_against_oracle(name):
 
 
 def test_plan_structure_cfg1():
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.plan import Plan
     prob = synth.make_config("cfg1")
     g = lambda a: torch.from_numpy(a).cuda()
@@ -99,7 +99,7 @@ def test_permuted_edges_give_same_answer():
 
 def test_strided_targets_view():
     """main/batrack.py:871 passes targets_3d[..., :2] (row stride 3)."""
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.lietorch import SE3
     from gpu_util import as_cuda
@@ -118,7 +118,7 @@ def test_strided_targets_view():
 
 
 def test_inputs_untouched_and_outputs_fresh():
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.lietorch import SE3
     from gpu_util import as_cuda
@@ -135,7 +135,7 @@ def test_inputs_untouched_and_outputs_fresh():
 
 
 def test_contract_errors():
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.lietorch import SE3
     from gpu_util import as_cuda
@@ -155,7 +155,7 @@ def test_contract_errors():
 
 def test_cholesky_failure_and_nan_are_silent():
     """ba.py:9-13: a failed factorisation leaves the poses unchanged; depths still move."""
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.lietorch import SE3
     from batrack_b200.plan import get_plan
@@ -179,7 +179,7 @@ def test_nan_retry_branch_matches_reference_semantics():
     elsewhere. (A retry that *repairs* dX needs an overflow inside the fp32 LAPACK solve; the fp64 band solver has no such
     case, so the branch is pinned on what both sides can reach.) BA (no retry in the reference, ba.py:205-207) must not
     set the bit."""
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA, BA_rgbd_droid
     from batrack_b200.lietorch import SE3
     from batrack_b200.plan import get_plan
@@ -213,7 +213,7 @@ def test_streaming_give_up_path_is_correct():
     and a stand-by launch redoes the solve on the finished system. Forced here on the headline graph with a spin bound of
     a few microseconds (BA_OPT_SPIN_CAP) and a Schur kernel throttled to one CTA per SM (BA_OPT_STREAM_SMEM_KB); the
     result must still match the fp64 oracle."""
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.lietorch import SE3
     from batrack_b200.plan import Plan
@@ -268,7 +268,8 @@ def test_se3_ops_match_reference():
 
 
 def test_reproject_matches_oracle():
-    from batrack_b200 import projective_ops as pops, synth
+    from batrack_b200 import projective_ops as pops
+    import synth
     from batrack_b200.lietorch import SE3
     from gpu_util import as_cuda
     ps, _ = synth.make_slam_problem(n_frames=21, patches_per_frame=32, seed=3)
@@ -284,7 +285,7 @@ def test_reproject_matches_oracle():
 def test_mid_graph_against_sparse_oracle():
     """64 keyframes / 16 384 tracks / 311 296 edges, 3 iterations, against the sparse-aware fp64 oracle
     (banded reduced system, n = 63)."""
-    from batrack_b200 import synth
+    import synth
     from gpu_util import run_ours
     prob = synth.make_config("mid")
     ws, so = [prob.weights] * 3, [False] * 3
@@ -299,7 +300,7 @@ def test_headline_graph_all_ten_iterations():
     """cfg3 (256 KF / 65 536 tracks / 1 245 184 edges, BASELINE.json configs[2]: 10 LM iterations): EVERY one of the 10
     chained iterations against the sparse fp64 oracle's results (tests/golden/cfg3_x10_sparse64.npz, produced by
     tests/golden/make_golden_large.py), plus the size-independent properties."""
-    from batrack_b200 import synth
+    import synth
     from gpu_util import run_ours
     prob = synth.make_config("cfg3")
     z = _golden_large("cfg3_x10_sparse64.npz")
@@ -322,7 +323,7 @@ def test_davis_like_window_against_dense_oracle():
     """cfg2 stand-in (configs/davis_demo.yaml shape: 400 patches / frame, S_slam 12, kf_stride 2, 15-pose
     optimisation window): the reference's own graph bookkeeping replayed on synthetic tracks, the update()
     pairing (pose call on weights_pose, structure-only call on weights) x 2, against the fp64 oracle."""
-    from batrack_b200 import synth
+    import synth
     from gpu_util import run_ours
     ps, w_all = synth.make_slam_problem(n_frames=25, patches_per_frame=400, seed=7, buffer_size=64)
     ws, so = [ps.weights, w_all] * 2, [False, True] * 2
@@ -338,7 +339,7 @@ def test_1024_keyframe_graph_against_sparse_oracle():
     with 6138 unknowns; poses and disparities of two chained iterations against the sparse fp64 oracle
     (tests/golden/cfg5_x2_sparse64.npz, produced by tests/golden/make_golden_large.py — the dense reference cannot hold
     this graph: 6.4 GB per E-sized temporary)."""
-    from batrack_b200 import synth
+    import synth
     from gpu_util import run_ours
     prob = synth.make_config("cfg5")
     z = _golden_large("cfg5_x2_sparse64.npz")
@@ -357,7 +358,7 @@ def test_sintel_like_full_sequence_window():
     """cfg4 stand-in (configs/sintel.yaml: 256 patches / frame, S_slam 12, kf_stride 2; "full-sequence" = the removal and
     optimisation windows cover all 50 frames, so 48 free poses and every keyframe step's 18 432 edges stay in the
     graph): the reference's own bookkeeping replayed on synthetic tracks, update() pairing x 2, against the fp64 oracle."""
-    from batrack_b200 import synth
+    import synth
     from gpu_util import run_ours
     ps, w_all = synth.make_slam_problem(n_frames=50, patches_per_frame=256, seed=4, buffer_size=64, opt_window=64,
                                         removal_window=64, width=1024, height=436, name="sintel_like")
@@ -371,7 +372,7 @@ def test_sintel_like_full_sequence_window():
 
 
 def test_structure_only_and_ba_variant_on_mid_graph():
-    from batrack_b200 import synth
+    import synth
     from gpu_util import run_ours
     prob = synth.make_config("mid")
     ws, so = [prob.weights] * 3, [True, False, True]
@@ -386,7 +387,7 @@ def test_structure_only_and_ba_variant_on_mid_graph():
 def test_fused_update_equals_call_sequence():
     """BA_update (one native call for the loop of main/batrack.py:869-875) against the same steps issued one by one
     and against the fp64 oracle."""
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA_update
     from batrack_b200.lietorch import SE3
     from gpu_util import as_cuda, run_ours
@@ -406,7 +407,8 @@ def test_fused_update_equals_call_sequence():
 
 def test_point_cloud_and_flow_mag_match_oracle():
     """The reprojection consumers next to BA (main/batrack.py:891-893, 1011-1018)."""
-    from batrack_b200 import projective_ops as pops, synth
+    from batrack_b200 import projective_ops as pops
+    import synth
     from batrack_b200.lietorch import SE3
     from gpu_util import as_cuda
     from oracle import se3_ops
@@ -441,7 +443,7 @@ def test_point_cloud_and_flow_mag_match_oracle():
 def test_host_buffer_pipeline_equals_device_call():
     """ba_step_host_async / ba_host_sync (pinned host arrays in and out, double-buffered staging): four pipelined
     steps with different weights give bitwise what BA_rgbd_droid gives on device tensors; ba_step_host likewise."""
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.host import HostBA
     from batrack_b200.lietorch import SE3
@@ -496,7 +498,7 @@ def test_band_solver_failure_is_silent_and_recoverable(n_kf, stream):
     """The band (DMMA) solver — plain at 64 keyframes, twisted over two CTAs at 112 (>= 64 tile columns) — launched
     behind the Schur kernel (default) or next to it (streaming hand-over, option "stream"): a failed factorisation (ba.py:9-13) leaves the poses unchanged
     while the depths still move, and the next call on the same plan is correct again (flags carry a new epoch)."""
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.lietorch import SE3
     from batrack_b200.plan import Plan
@@ -532,7 +534,7 @@ def test_ba_step_replays_from_a_cuda_graph(stream):
     """the step must be graph-capturable. A captured BA_rgbd_droid call (plain, and with the band solver
     streamed next to the Schur kernel: cross-stream events, no host-side per-call state) is replayed on new weights and
     matches eager calls."""
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.lietorch import SE3
     from batrack_b200.plan import Plan
@@ -573,7 +575,7 @@ def test_every_band_solver_matches_the_oracle(n_kf):
     """The reduced solve has four implementations behind BA_OPT_SOLVER (shared-memory tile solver: short systems and
     bands up to 145; DMMA band solver: long bands up to 120; scalar window solver; automatic choice). On one graph they
     must all land on the fp64 oracle's result, and a failed factorisation (ba.py:9-13) must leave the poses alone."""
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.lietorch import SE3
     from batrack_b200.plan import Plan

@@ -41,7 +41,7 @@ def test_transform_jacobian_and_depth_match_reference():
 
 def test_print_path_reports_the_reference_residual(capsys):
     """BA_rgbd_droid(PRINT=True) prints the mean masked residual norm of ba.py:244-245."""
-    from batrack_b200 import synth
+    import synth
     from batrack_b200.ba import BA_rgbd_droid
     from batrack_b200.lietorch import SE3
     from gpu_util import as_cuda
@@ -62,7 +62,8 @@ def test_print_path_reports_the_reference_residual(capsys):
 
 def test_point_cloud_back_proj_and_proj_to_frames():
     """The point-cloud refresh next to BA (main/batrack.py:440-444, 821-854, 891-893)."""
-    from batrack_b200 import projective_ops as pops, synth
+    from batrack_b200 import projective_ops as pops
+    import synth
     from batrack_b200.lietorch import SE3
     from gpu_util import as_cuda
     from oracle import se3_ops

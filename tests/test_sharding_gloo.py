@@ -24,7 +24,7 @@ def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from batrack_b200 import synth
+    import synth
     from oracle import ba_oracle
     n_kf = synth.CONFIGS["cfg1"][0]
     lo, hi = (n_kf * rank) // world, (n_kf * (rank + 1)) // world

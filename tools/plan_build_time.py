@@ -4,7 +4,7 @@ capacity plan (device-side re-derivation, no synchronisation, no allocation): cf
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from batrack_b200 import synth
+import synth
 from batrack_b200.plan import CapacityPlan, Plan
 
 for name in sys.argv[1:] or ["davis", "cfg3"]:

@@ -3,7 +3,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from batrack_b200 import synth
+import synth
 from batrack_b200.ba import BA_rgbd_droid
 from batrack_b200.lietorch import SE3
 from batrack_b200.plan import Plan

@@ -4,7 +4,7 @@ is relative to the moment the factor warp publishes W_J. python tools/solver_tim
 import os, sys
 sys.path.insert(0, "/root/repo")
 import numpy as np, torch
-from batrack_b200 import synth
+import synth
 from batrack_b200.ba import BA_rgbd_droid
 from batrack_b200.lietorch import SE3
 from batrack_b200.plan import Plan
