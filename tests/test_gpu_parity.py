@@ -603,3 +603,51 @@ def test_every_band_solver_matches_the_oracle(n_kf):
         assert rel_err(Gf.data.cpu().numpy(), t["poses"].cpu().numpy()) < 1e-6, sv
         G2, _ = call(prob.ep)
         assert plan.status() == 0 and rel_err(G2.data.cpu().numpy(), G.data.cpu().numpy()) < 1e-6, sv
+
+
+@pytest.mark.parametrize("cfg,world", [("cfg1", 2), ("mid", 4)])
+def test_sharded_assemble_and_solve_through_the_c_abi(cfg, world):
+    """SURVEY.md §8e on hardware without a second GPU: `world` keyframe-window shards of one graph, each with its own plan
+    on the same device, go through the sharded entry points — ba_plan_set_layout (agreed pose count / band width),
+    ba_assemble (partial [S | y]), the exchange (here a plain sum of the ranks' exchange buffers, what the NCCL
+    all-reduce computes), ba_solve_update — and the merged result must match the fp64 oracle of the full graph."""
+    import ctypes as C
+    import synth
+    from batrack_b200 import _capi
+    from batrack_b200.ba import _problem
+    from batrack_b200.lietorch import SE3
+    from batrack_b200.plan import Plan
+    from gpu_util import as_cuda
+    n_kf = synth.CONFIGS[cfg][0]
+    full = synth.make_config(cfg)
+    shards = [synth.make_config(cfg, kf_lo=(n_kf * r) // world, kf_hi=(n_kf * (r + 1)) // world) for r in range(world)]
+    ts = [as_cuda(sh) for sh in shards]
+    N, NM = ts[0]["poses"].shape[1], ts[0]["patches"].shape[1]
+    plans = [Plan(t["ii"], t["jj"], t["kk"], N, NM) for t in ts]
+    n_total, bwb = max(p.info.n_total for p in plans), max(p.info.block_bandwidth for p in plans)
+    for p in plans:
+        p.set_layout(n_total, bwb)
+    L, st = _capi.lib(), _capi.stream_ptr(torch.device("cuda:0"))
+    probs = []
+    for sh, t, p in zip(shards, ts, plans):
+        w = torch.from_numpy(sh.weights).cuda()[None]
+        probs.append(_problem(p, SE3(t["poses"]), t["patches"], t["patches_monodisp"], t["intrinsics"], t["targets_2d"], w, sh.lmbda,
+                              sh.bounds, sh.ep, sh.fixedp, False, sh.loss, sh.alpha))
+        _capi.check(L.ba_assemble(p.handle, C.byref(probs[-1][0]), st), "ba_assemble")
+    bufs = [p.reduced_system() for p in plans]
+    assert len({b.numel() for b in bufs}) == 1                      # the same layout on every rank
+    total = torch.stack(bufs).sum(0)
+    for b in bufs:
+        b.copy_(total)
+    disp = ts[0]["patches"][0, :, 2, 0, 0].clamp(1e-3, 10.0).double()
+    base = disp.clone()
+    poses = None
+    for sh, p, pr in zip(shards, plans, probs):
+        _capi.check(L.ba_solve_update(p.handle, C.byref(pr[0]), st), "ba_solve_update")
+        assert p.status() == 0
+        disp += pr[2][0, :, 2, 0, 0].double() - base               # every rank moves its own tracks only
+        poses = pr[1] if poses is None else poses
+        assert torch.equal(poses, pr[1])                            # replicated solve: bitwise identical
+    P64, D64 = _oracle().run_sequence(full, [full.weights], [False], torch.float64, mode="sparse")
+    assert rel_err(poses[0].cpu().numpy(), P64[0]) < TOL
+    assert rel_err(disp.cpu().numpy(), D64[0]) < TOL
