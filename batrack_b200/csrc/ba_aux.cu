@@ -355,7 +355,14 @@ int host_pipe_get(BaPlan *pl, size_t total, HostPipe **out) {
     BA_CUDA(cudaMalloc((void **)&hp->stage[1], total));
     hp->bytes = total;
   }
-  if (hp->bytes < total) return BA_ERR_ARG;            // the plan fixes N, NM, E, m: cannot happen
+  if (hp->bytes < total) {                             // a capacity plan re-derived for a larger graph: grow the slots
+    BA_CUDA(cudaDeviceSynchronize());
+    for (int k = 0; k < 2; ++k) { BA_CUDA(cudaFree(hp->stage[k])); hp->stage[k] = nullptr; }
+    BA_CUDA(cudaMalloc((void **)&hp->stage[0], total));
+    BA_CUDA(cudaMalloc((void **)&hp->stage[1], total));
+    hp->bytes = total;
+    hp->seq = 0; hp->pre_mask = 0; hp->pre_waited = false;
+  }
   *out = hp;
   return BA_OK;
 }
