@@ -354,7 +354,10 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) k_edge_pass(PlanView pv, Call
 //     in fp64, maps them to the i side (Bii = A Bjj A^T, Bij = -A Bjj, vi = -A vj, A = Ad(Gij)^T) and issues the
 //     fp64 atomics, with Bii / vi pre-summed over the positions (they all hit the same pose block).
 // =================================================================================================
-constexpr int kE2PosBlock = 32;                 // positions per block (constants / per-position sums staged per block)
+constexpr int kE2PosBlock = 32;                 // positions per block (constants / per-position sums staged per block) ...
+constexpr int kE2PosBlockWide = 96;             // ... and on small graphs (>= 4 position splits, <= 2 track slices per CTA), where the
+                                                // per-block set-up and flush (8 k cycles) would otherwise be paid three times per track
+__host__ __device__ constexpr int e2_pos_block(int kp) { return kp >= 4 ? kE2PosBlockWide : kE2PosBlock; }
 // TPL = tracks per lane. 1: lane <-> track. 2 (large graphs): a lane walks tracks t and t + 32 together — the per-position
 // constants, the control flow and the 27-value transpose reduction are shared by two edges, and the two independent edge
 // computations give the in-order warp instruction-level parallelism (the kernel is bound by instruction issue, not HBM).
@@ -369,8 +372,8 @@ constexpr int kE2FlushPos = (kEdge2Warps * kE2WarpScratch * 4) / ((kAccComps + 3
                                 ? (kEdge2Warps * kE2WarpScratch * 4) / ((kAccComps + 36 + kFlushOuts) * 8) : kE2PosBlock;
 // dynamic shared memory: per warp scratch, per track slice (KT = kEdge2Warps / KP) the per-position sums, constants
 static size_t edge2_smem_bytes(int kp, int tpl) {
-  return (size_t)(kEdge2Warps * e2_warp_scratch(tpl) + (kEdge2Warps / kp) * kE2PosBlock * kE2AccStride +
-                  kE2PosBlock * kPosFloats + 5 * kE2PosBlock + 8) * sizeof(float);
+  const int PB = e2_pos_block(kp);
+  return (size_t)(kEdge2Warps * e2_warp_scratch(tpl) + (kEdge2Warps / kp) * PB * kE2AccStride + PB * kPosFloats + 5 * PB + 8) * sizeof(float);
 }
 static_assert(kE2FlushPos >= 1, "flush scratch too small");
 static_assert(kEdge2Warps * 8 * 64 <= kEdge2Warps * kE2WarpScratch, "per-track partials alias the scratch");
@@ -399,14 +402,15 @@ __global__ void __launch_bounds__(kE2Threads, TPL == 2 ? 2 : 3) k_edge_pass_v2(P
   float *red = scratch + warp * kWarpScratch;                      // [27][36]
   float2 *stage = reinterpret_cast<float2 *>(red + kAccComps * kE2RedStride);   // [2][2][32][slice + 1]
   float *sacc_all = scratch + kEdge2Warps * kWarpScratch;          // [track slice][32][28]
-  float *sacc = sacc_all + ks * (kE2PosBlock * kE2AccStride);
-  float *sconst = sacc_all + (kEdge2Warps / KP) * (kE2PosBlock * kE2AccStride); // [32][20]
-  int *slj = reinterpret_cast<int *>(sconst + kE2PosBlock * kPosFloats);        // [32 + 1] target slot of the position (+ look-ahead)
-  int *sfj = slj + kE2PosBlock + 1;                                             // [32] target pose free?
-  int *spp = sfj + kE2PosBlock;                                                 // [32] pattern position (edge offset in the track)
-  int *spj = spp + kE2PosBlock;                                                 // [32] target pose
-  int *hlist = spj + kE2PosBlock;                                               // [32] block positions that start a slot run
-  int *s_ctl = hlist + kE2PosBlock;                                             // [0] positions in this block, [1] run heads
+  const int PB = e2_pos_block(KP);                                 // positions per block
+  float *sacc = sacc_all + ks * (PB * kE2AccStride);
+  float *sconst = sacc_all + (kEdge2Warps / KP) * (PB * kE2AccStride);          // [PB][20]
+  int *slj = reinterpret_cast<int *>(sconst + PB * kPosFloats);                 // [PB + 1] target slot of the position (+ look-ahead)
+  int *sfj = slj + PB + 1;                                                      // [PB] target pose free?
+  int *spp = sfj + PB;                                                          // [PB] pattern position (edge offset in the track)
+  int *spj = spp + PB;                                                          // [PB] target pose
+  int *hlist = spj + PB;                                                        // [PB] block positions that start a slot run
+  int *s_ctl = hlist + PB;                                                      // [0] positions in this block, [1] run heads
 
   const int tw0 = t0 + 32 * TPL * ks;                              // first track of this warp's slice (lane: tracks tw0 + lane [+ 32])
   const bool warp_has = tw0 < t1;
@@ -435,19 +439,24 @@ __global__ void __launch_bounds__(kE2Threads, TPL == 2 ? 2 : 3) k_edge_pass_v2(P
   const int *ps = pv.pat_ps + pat0;
   for (int pb = 0; pb < d;) {
     __syncthreads();                                               // previous block's flush is done with the scratch
-    if (tau <= kE2PosBlock) {
+    if (tau <= PB) {
       int lj = -1;
-      if (pb + tau < d) { const int p = ps[pb + tau]; lj = pv.pat_lj[pat0 + p]; if (tau < kE2PosBlock) spp[tau] = p; }
+      if (pb + tau < d) { const int p = ps[pb + tau]; lj = pv.pat_lj[pat0 + p]; if (tau < PB) spp[tau] = p; }
       slj[tau] = lj;
     }
     __syncthreads();
     if (warp == 0) {
-      int e = min(kE2PosBlock, d - pb);
+      int e = min(PB, d - pb);
       if (pb + e < d) { while (e > 1 && slj[e] == slj[e - 1]) --e; }           // runs are <= kMaxSlotRun < 32 long
-      const bool head = lane < e && (lane == 0 || slj[lane] != slj[lane - 1]);
-      const unsigned hm = __ballot_sync(0xffffffffu, head);
-      if (head) hlist[__popc(hm & ((1u << lane) - 1u))] = lane;
-      if (lane == 0) { s_ctl[0] = e; s_ctl[1] = __popc(hm); }
+      int nhd = 0;
+      for (int x0 = 0; x0 < e; x0 += 32) {                                      // run heads, in order
+        const int x = x0 + lane;
+        const bool head = x < e && (x == 0 || slj[x] != slj[x - 1]);
+        const unsigned hm = __ballot_sync(0xffffffffu, head);
+        if (head) hlist[nhd + __popc(hm & ((1u << lane) - 1u))] = x;
+        nhd += __popc(hm);
+      }
+      if (lane == 0) { s_ctl[0] = e; s_ctl[1] = nhd; }
     }
     __syncthreads();
     const int np = s_ctl[0], nh = s_ctl[1];
@@ -622,7 +631,7 @@ __global__ void __launch_bounds__(kE2Threads, TPL == 2 ? 2 : 3) k_edge_pass_v2(P
         for (int x = tau; x < nq * kAccComps; x += NT) {
           const int pl = x / kAccComps, k = x - pl * kAccComps;
           double sv = 0.0;
-          for (int ww = 0; ww < nS; ++ww) sv += (double)sacc_all[(ww * kE2PosBlock + hlist[fb + pl]) * kE2AccStride + k];
+          for (int ww = 0; ww < nS; ++ww) sv += (double)sacc_all[(ww * PB + hlist[fb + pl]) * kE2AccStride + k];
           sumD[x] = sv;
         }
         __syncthreads();
@@ -1392,10 +1401,13 @@ namespace ba {
 int kernels_prepare_device() {
   BA_CUDA(cudaFuncSetAttribute(k_edge_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
   BA_CUDA(cudaFuncSetAttribute(k_edge_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEdgeSmemBytes));
-  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1, 1)));
-  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1, 1)));
-  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1, 2)));
-  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge2_smem_bytes(1, 2)));
+  size_t e2max[3] = {0, 0, 0};
+  for (int tpl = 1; tpl <= 2; ++tpl)
+    for (int kp = 1; kp <= kEdge2Warps; kp *= 2) e2max[tpl] = std::max(e2max[tpl], edge2_smem_bytes(kp, tpl));
+  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e2max[1]));
+  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e2max[1]));
+  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e2max[2]));
+  BA_CUDA(cudaFuncSetAttribute(k_edge_pass_v2<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e2max[2]));
   BA_CUDA(cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   BA_CUDA(cudaFuncSetAttribute(k_solve_window, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
   BA_CUDA(cudaFuncSetAttribute(k_solve_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
