@@ -73,9 +73,10 @@ def _problem(plan, poses, patches, monodisp, intrinsics, targets, weights, lmbda
     for k in range(4):
         p.bounds[k] = float(bounds[k])
     p.fixedp, p.structure_only, p.loss = int(fixedp), int(bool(structure_only)), _capi.LOSS_IDS[loss]
-    poses_out = torch.empty((1, N, 7), dtype=torch.float32, device=pdata.device)
+    # a structure-only call returns the caller's poses object, like the reference (ba.py:336-339): nothing to allocate or copy
+    poses_out = None if structure_only else torch.empty((1, N, 7), dtype=torch.float32, device=pdata.device)
     patches_out = torch.empty((1, NM, 3, 1, 1), dtype=torch.float32, device=pdata.device)
-    p.poses_out, p.patches_out = poses_out.data_ptr(), patches_out.data_ptr()
+    p.poses_out, p.patches_out = (poses_out.data_ptr() if poses_out is not None else None), patches_out.data_ptr()
     return p, poses_out, patches_out, keep
 
 
@@ -125,7 +126,7 @@ def _run(poses, patches, monodisp, intrinsics, targets, weights, lmbda, ii, jj, 
                 dist.all_reduce(plan.reduced_system(), op=dist.ReduceOp.SUM, group=group)
             _capi.check(L.ba_solve_update(plan.handle, C.byref(prob), st), "ba_solve_update")
     del keep
-    return SE3(poses_out), patches_out
+    return (SE3(poses_out) if poses_out is not None else poses), patches_out
 
 
 def BA_rgbd_droid(poses, patches, patches_monodisp, intrinsics, targets_2d, targets_disp, weights, lmbda, ii, jj, kk,
@@ -166,4 +167,4 @@ def BA_update(poses, patches, patches_monodisp, intrinsics, targets_2d, weights_
         _capi.check(_capi.lib().ba_update(plan.handle, C.byref(prob), _capi.ptr(w_all), int(iters),
                                           _capi.stream_ptr(pdata.device)), "ba_update")
     del keep
-    return SE3(poses_out), patches_out
+    return (SE3(poses_out) if poses_out is not None else poses), patches_out

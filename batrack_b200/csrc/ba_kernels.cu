@@ -1518,10 +1518,11 @@ static int solve_update_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int
   CallView cv;
   int rc = make_call(pl, pb, &cv);
   if (rc) return rc;
-  if (!pb->poses_out || !pb->patches_out) return BA_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream_;
   const PlanView &pv = pl->v;
   const bool so = pb->structure_only || cv.n == 0;
+  // a structure-only call leaves the poses alone (ba.py:336-339 returns the caller's object): poses_out may be NULL then
+  if ((!pb->poses_out && !so) || !pb->patches_out) return BA_ERR_ARG;
   if (!so && solved) {
     // join the streaming solve; the stand-by launch behind it does the solve only if that one gave up (kernels
     // serialised by a profiler / sanitizer: its producer never ran next to it)
@@ -1552,7 +1553,8 @@ static int solve_update_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int
     k_backsub<<<nb_trk + nb_cp + nb_retr, 256, 0, s>>>(pv, cv, so ? 0 : 1, nb_trk, nb_cp, so ? 0 : pv.N); BA_LAUNCH_CHECK();
   }
   BA_MARK(pl, BA_STAGE_RETR, s);
-  if (so) BA_CUDA(cudaMemcpyAsync(pb->poses_out, pb->poses, (size_t)pv.N * 7 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (so && pb->poses_out && pb->poses_out != pb->poses)
+    BA_CUDA(cudaMemcpyAsync(pb->poses_out, pb->poses, (size_t)pv.N * 7 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   BA_MARK(pl, BA_N_STAGES, s);
   return BA_OK;
 }
@@ -1598,16 +1600,18 @@ extern "C" int ba_update(BaPlan *pl, const BaProblem *pb, const float *weights_a
   BaProblem cur = *pb;
   const int total = 2 * iters;
   for (int c = 0; c < total; ++c) {
-    const bool last = c == total - 1;
-    float *po = last ? pb->poses_out : pl->pp_buf[c & 1];
+    const bool so = (c & 1) != 0;                       // main/batrack.py:871-872 then :874-875
+    const bool last_pose_call = c == total - 2, last = c == total - 1;
+    // the structure-only calls leave the poses where they are (no copy); the last pose call writes the caller's buffer
+    float *po = so ? nullptr : (last_pose_call ? pb->poses_out : pl->pp_buf[(c >> 1) & 1]);
     float *qo = last ? pb->patches_out : pl->pp_buf[c & 1] + np;
     cur.poses_out = po;
     cur.patches_out = qo;
-    cur.structure_only = c & 1;                        // main/batrack.py:871-872 then :874-875
-    cur.weights = (c & 1) ? weights_all : pb->weights;
+    cur.structure_only = so ? 1 : 0;
+    cur.weights = so ? weights_all : pb->weights;
     int rc = ba_step(pl, &cur, stream);
     if (rc) return rc;
-    cur.poses = po;
+    if (!so) cur.poses = po;
     cur.patches = qo;
   }
   return BA_OK;

@@ -80,7 +80,8 @@ typedef struct {
   int32_t loss;              /* BA_LOSS_* */
   int32_t targets_stride;    /* floats between consecutive targets rows: 2, or 3 when the caller passes the
                                 view targets_3d[...,:2] (main/batrack.py:871); 0 means 2 */
-  float *poses_out;          /* returned poses.data [1,N,7] (fresh buffer; may NOT alias poses) */
+  float *poses_out;          /* returned poses.data [1,N,7] (fresh buffer; may NOT alias poses). A structure-only call leaves the
+                                poses alone (ba.py:336-339): NULL is allowed then and nothing is copied */
   float *patches_out;        /* returned patches    [1,NM,3,1,1] (fresh buffer) */
 } BaProblem;
 
