@@ -159,6 +159,14 @@ struct BaPlan {
   float2 *Cw, *Qw;
   int *status;
   int64_t sy_floats;                   // capacity of SY (elements)
+  // The reduced system is double-buffered when it is small: the back-substitution kernel of a call clears the OTHER buffer
+  // for the next call (no memset node in steady state: ~6 us per call), while [S | y] of the call itself stay readable
+  // (ba_plan_debug_dense, sharded exchange). sy_clean[b] = leading bytes of buffer b known to be zero.
+  double *SY2;
+  int sy_cur;
+  int64_t sy_clean[2];
+  int sy_untracked;                    // a call on this plan was captured into a CUDA graph: replays dirty buffers unseen
+  double *sy_last;                     // buffer of the last call that assembled a system
   int64_t est_floats;                  // size of Est
   int last_n, last_fixedp;             // layout of the last ba_assemble
   float *pp_buf[2];                    // ping-pong (poses | patches) buffers of ba_update

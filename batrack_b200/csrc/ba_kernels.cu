@@ -1276,9 +1276,16 @@ __device__ __forceinline__ void pose_retr_one(const CallView &cv, int i) {
 //   [nb_trk, nb_trk+nb_cp) one thread per patch: patches without a track are copied with the clamp;
 //   beyond                 pose retraction T <- Exp(dx) T for every pose of the buffer, dx = 0 outside the window
 //                          (ba.py:47-49,336-337; lietorch/groups.py:153-156), when retr_n > 0
-__global__ void __launch_bounds__(256) k_backsub(PlanView pv, CallView cv, int use_dx, int nb_trk, int nb_cp, int retr_n) {
+__global__ void __launch_bounds__(256) k_backsub(PlanView pv, CallView cv, int use_dx, int nb_trk, int nb_cp, int nb_retr, int retr_n,
+                                                 double2 *__restrict__ zero_ptr, long long zero_n16, int nb_zero) {
   __shared__ double part[8][32];
   const int bid = blockIdx.x;
+  if (bid >= nb_trk + nb_cp + nb_retr) {                           // clear the next call's reduced system (the other buffer)
+    const double2 z2 = make_double2(0.0, 0.0);
+    for (long long i = (long long)(bid - nb_trk - nb_cp - nb_retr) * blockDim.x + threadIdx.x; i < zero_n16; i += (long long)nb_zero * blockDim.x)
+      zero_ptr[i] = z2;
+    return;
+  }
   if (bid >= nb_trk + nb_cp) {
     const int i = (bid - nb_trk - nb_cp) * blockDim.x + threadIdx.x;
     if (i < retr_n) pose_retr_one(cv, i);
@@ -1361,7 +1368,8 @@ static int make_call(BaPlan *pl, const BaProblem *pb, CallView *cv) {
   int n, bw, ld, off; int64_t sf;
   layout_for(pl, pb->fixedp, &n, &bw, &ld, &off, &sf);
   cv->n = n; cv->M = 6 * n; cv->ld = ld; cv->off = off; cv->bw = bw;
-  cv->S = pl->SY; cv->y = pl->SY + sf;
+  double *sy = (pl->sy_cur && pl->SY2) ? pl->SY2 : pl->SY;        // the buffer of this call (toggled when a call has solved)
+  cv->S = sy; cv->y = sy + sf;
   cv->Est = pl->Est; cv->Cw = pl->Cw; cv->Qw = pl->Qw; cv->dX = pl->dX; cv->dZ = pl->dZ; cv->L = pl->L;
   cv->status = pl->status;
   cv->poses_out = pb->poses_out; cv->patches_out = pb->patches_out;
@@ -1448,7 +1456,17 @@ static int assemble_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int str
     BA_MARK(pl, BA_STAGE_ZERO, s);
     // streaming: the completion flags of the Schur units sit right behind y and are cleared by the same memset (no
     // per-call state on the host: a captured CUDA graph of this call can be replayed)
-    BA_CUDA(cudaMemsetAsync(cv.S, 0, (size_t)((cv.y - cv.S) + cv.M) * sizeof(double) + (streaming ? (size_t)pv.n_ounits * sizeof(int) : 0), s));
+    {
+      // skipped when the previous call's back-substitution kernel has already cleared this buffer (solve_update_impl)
+      const size_t zbytes = (size_t)((cv.y - cv.S) + cv.M) * sizeof(double) + (streaming ? (size_t)pv.n_ounits * sizeof(int) : 0);
+      const int b = (pl->sy_cur && pl->SY2) ? 1 : 0;
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      BA_CUDA(cudaStreamIsCapturing(s, &cs));
+      if (cs != cudaStreamCaptureStatusNone) pl->sy_untracked = 1;
+      if (pl->sy_untracked || (size_t)pl->sy_clean[b] < zbytes) BA_CUDA(cudaMemsetAsync(cv.S, 0, zbytes, s));
+      pl->sy_clean[b] = 0;
+      pl->sy_last = cv.S;
+    }
     if (streaming) {
       BA_CUDA(cudaEventRecord(pl->ev_step_begin, s));               // flags cleared; the previous call's back-substitution (reads dX) is behind
       BA_CUDA(cudaStreamWaitEvent(pl->solve_stream, pl->ev_step_begin, 0));
@@ -1508,7 +1526,7 @@ extern "C" int ba_plan_reduced_system(const BaPlan *pl, double **ptr, int64_t *n
   if (!pl || !ptr || !n_floats || pl->last_fixedp < 0) return BA_ERR_ARG;
   int n, bw, ld, off; int64_t sf;
   layout_for(pl, pl->last_fixedp, &n, &bw, &ld, &off, &sf);
-  *ptr = pl->SY;
+  *ptr = (pl->sy_cur && pl->SY2) ? pl->SY2 : pl->SY;             // the buffer ba_assemble has just filled
   *n_floats = sf + 6 * (int64_t)n;
   return BA_OK;
 }
@@ -1550,7 +1568,21 @@ static int solve_update_impl(BaPlan *pl, const BaProblem *pb, void *stream_, int
   BA_MARK(pl, BA_STAGE_BACKSUB, s);
   {
     const int nb_trk = (pv.m + 31) / 32, nb_cp = (pv.NM + 255) / 256, nb_retr = so ? 0 : (pv.N + 255) / 256;
-    k_backsub<<<nb_trk + nb_cp + nb_retr, 256, 0, s>>>(pv, cv, so ? 0 : 1, nb_trk, nb_cp, so ? 0 : pv.N); BA_LAUNCH_CHECK();
+    // a call that solved hands the next one a cleared reduced system: the other buffer, zeroed by spare blocks here
+    double *zero_ptr = nullptr;
+    long long zero_n16 = 0;
+    if (!so && pl->SY2 && !pl->sy_untracked) {
+      const int other = pl->sy_cur ? 0 : 1;
+      const size_t zbytes = ((size_t)((cv.y - cv.S) + cv.M) * sizeof(double) + (size_t)pv.n_ounits * sizeof(int) + 15) & ~(size_t)15;
+      zero_ptr = other ? pl->SY2 : pl->SY;
+      zero_n16 = (long long)(zbytes / 16);
+      pl->sy_clean[other] = (int64_t)zbytes;
+      pl->sy_cur = other;
+    }
+    const int nb_zero = zero_ptr ? (int)std::min<long long>((zero_n16 + 2047) / 2048, 148) : 0;
+    k_backsub<<<nb_trk + nb_cp + nb_retr + nb_zero, 256, 0, s>>>(pv, cv, so ? 0 : 1, nb_trk, nb_cp, nb_retr, so ? 0 : pv.N,
+                                                                  reinterpret_cast<double2 *>(zero_ptr), zero_n16, nb_zero);
+    BA_LAUNCH_CHECK();
   }
   BA_MARK(pl, BA_STAGE_RETR, s);
   if (so && pb->poses_out && pb->poses_out != pb->poses)
@@ -1625,8 +1657,9 @@ extern "C" int ba_plan_debug_dense(const BaPlan *pl, int32_t n, float *S, float 
   layout_for(pl, pl->last_fixedp, &nn, &bw, &ld, &off, &sf);
   if (n != nn) return BA_ERR_ARG;
   const int M = 6 * nn;
-  if (S && M > 0) { k_debug_dense<<<(M * M + 255) / 256, 256, 0, s>>>(pl->SY, M, ld, off, bw, S); BA_LAUNCH_CHECK(); }
-  if (y && M > 0) { k_debug_cast<<<(M + 255) / 256, 256, 0, s>>>(pl->SY + sf, y, M); BA_LAUNCH_CHECK(); }
+  const double *sy = pl->sy_last ? pl->sy_last : pl->SY;           // [S | y] of the last call that assembled one
+  if (S && M > 0) { k_debug_dense<<<(M * M + 255) / 256, 256, 0, s>>>(sy, M, ld, off, bw, S); BA_LAUNCH_CHECK(); }
+  if (y && M > 0) { k_debug_cast<<<(M + 255) / 256, 256, 0, s>>>(sy + sf, y, M); BA_LAUNCH_CHECK(); }
   if (dX && M > 0) { k_debug_cast<<<(M + 255) / 256, 256, 0, s>>>(pl->dX, dX, M); BA_LAUNCH_CHECK(); }
   const int m = pl->v.m;
   if (Q) BA_CUDA(cudaMemcpy2DAsync(Q, sizeof(float), pl->Qw, sizeof(float2), sizeof(float), m, cudaMemcpyDeviceToDevice, s));

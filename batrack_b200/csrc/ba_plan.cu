@@ -591,6 +591,9 @@ static int alloc_workspace(BaPlan *pl) {
   int64_t need = sf + 6 * (int64_t)n + 8 + (pl->v.n_ounits + 1) / 2 + 2;     // [S | y | completion flags of the streaming Schur units]
   if (need > pl->sy_floats) {
     BA_CUDA(own(pl, &pl->SY, need));
+    pl->SY2 = nullptr;
+    if ((size_t)need * sizeof(double) <= ((size_t)64 << 20)) BA_CUDA(own(pl, &pl->SY2, need));
+    pl->sy_cur = 0; pl->sy_clean[0] = pl->sy_clean[1] = 0; pl->sy_last = nullptr;
     BA_CUDA(own(pl, &pl->L, sf + 8));
     BA_CUDA(own(pl, &pl->dX, 6 * (size_t)n + 8));
     BA_CUDA(own(pl, &pl->Wg, std::max(solve_mma_scratch_doubles(6 * n, std::min(bw, kMmaMaxBw)), solve_tiles_scratch_doubles(6 * n, bw)) + 64));   // solver scratch
@@ -817,6 +820,7 @@ static BaPlan *new_plan(int32_t N, int32_t NM, cudaStream_t s, int dev) {
   pl->v.N = N; pl->v.NM = NM;
   pl->device = dev;
   pl->SY = pl->L = pl->dX = pl->Wg = nullptr;
+  pl->SY2 = nullptr; pl->sy_cur = 0; pl->sy_clean[0] = pl->sy_clean[1] = 0; pl->sy_untracked = 0; pl->sy_last = nullptr;
   pl->Est = pl->dZ = nullptr;
   pl->Cw = pl->Qw = nullptr;
   pl->status = nullptr;
