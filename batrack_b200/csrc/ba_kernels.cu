@@ -1387,7 +1387,7 @@ using namespace ba;
 // from ~33 tile columns on a band <= 120 the band solver wins (378 unknowns: 113 us vs 134).
 constexpr int kTileSolverMaxCols = 32;
 static bool band_solver_covers(const CallView &cv) {
-  return cv.ld != cv.M && cv.bw <= kMmaMaxBw && std::max(solve_mma_smem_bytes(cv.M), solve_diag_smem_bytes(cv.M)) <= 227 * 1024 - 256;
+  return cv.ld != cv.M && cv.bw <= kMmaMaxBw && std::max(solve_mma_smem_bytes(cv.M), solve_diag_smem_bytes(cv.M)) <= 227 * 1024 - 1024;
 }
 static bool tile_solver_applies(const BaPlan *pl, const CallView &cv) {
   if (pl->opt.solver != 0 && pl->opt.solver != 4) return false;

@@ -22,6 +22,7 @@
 // tile (J+1,J+1), adds the damping and hands it to the factor warp: [A] of column J+1 overlaps [P]/[U] of column J.
 // Twist (two CTAs eliminating from both ends), streaming hand-over from the Schur kernel, stage-format factor and
 // the bulk-copy back substitution are those of DESIGN.md §4 K3.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -49,7 +50,11 @@ constexpr int kBarX = 8;                      // x_J of the back substitution
 constexpr int kBarZ = 9;                      // twist hand-over: z of the middle complete (tile warps)
 constexpr int kBarN = 10;                     // 10, 11: tile (J+1,J+1) without column J's update shipped (warp of diagonal 0 -> factor warp)
 constexpr int kCntP = 32 * (kNW + kNP), kCntA = 32 * (kNW + kNP + 1), kCntW = 32 * (kNP + 1);
-constexpr int kBackStages = 4;                // tile rows of L in flight during the back substitution
+constexpr int kLs = 132;                       // doubles per row of the stage-format factor in global memory (128 + 4 of padding)
+constexpr int kStRow = kLs * 8;                   // bytes between the rows of a staged tile row: rows 0,2,4,6 (1,3,5,7) of a tile
+                                              // start 64 bytes apart modulo 128: a B-fragment load takes the minimum two wavefronts
+constexpr int kStSlot = 8 * kStRow;           // one staged tile row
+constexpr int kNear = 3;                      // tile distances the chain warp of the back substitution keeps to itself
 constexpr int kPs = 12;                       // row stride (doubles) of the shared diagonal tile
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b, double c0, double c1) {
@@ -81,6 +86,34 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ---- shared-memory / mbarrier accessors on 32-bit shared addresses with immediate offsets: the back substitution's
+//      chain warp is bound by its instruction count (a lone warp issues every ~6 cycles), so no address is recomputed
+template <int OFF> __device__ __forceinline__ double lds64o(unsigned a) {
+  double v; asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF)); return v;
+}
+template <int OFF> __device__ __forceinline__ double2 lds128o(unsigned a) {
+  double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(OFF)); return v;
+}
+template <int OFF> __device__ __forceinline__ void sts128o(unsigned a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "d"(x), "d"(y) : "memory");
+}
+template <int OFF> __device__ __forceinline__ unsigned mbar_test_o(unsigned a, unsigned par) {
+  unsigned done;
+  asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.test_wait.parity.shared::cta.b64 P1, [%1+%2], %3;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+               : "=r"(done) : "r"(a), "n"(OFF), "r"(par) : "memory");
+  return done;
+}
+template <int OFF> __device__ __forceinline__ void mbar_wait_o(unsigned a, unsigned par) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1+%2], %3;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(done) : "r"(a), "n"(OFF), "r"(par) : "memory");
+  }
+}
+template <int OFF> __device__ __forceinline__ void mbar_arrive_o(unsigned a) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+%1];" ::"r"(a), "n"(OFF) : "memory");
+}
+
 }  // namespace
 
 // twist != 0: launched as a cluster of two CTAs. CTA 0 eliminates tile columns [0, Jm0) of the matrix, CTA 1 the
@@ -89,7 +122,7 @@ __device__ __forceinline__ void cluster_sync() {
 // both back-substitute their side in parallel. Exchange through global scratch XD + cluster barriers.
 __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv, int allow_retry, double *__restrict__ L_all,
                                                                    double *__restrict__ XD, int *__restrict__ gfl, int twist,
-                                                                   long long *__restrict__ trace, SolveFeed feed) {
+                                                                   long long *__restrict__ trace, SolveFeed feed, int rlog) {
   extern __shared__ __align__(16) double dsm[];
   // mode 2: stand-by launch behind a streaming one — runs only if that one gave up (its producer was not running
   // concurrently: kernels serialised by a profiler / sanitizer), as a plain solve of the by now complete system
@@ -112,8 +145,7 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
   // This side's factor in "stage format": 128 doubles per row; row r of tile row T = r / 8 holds L(r, c) for the 120
   // columns c in [8 (T - 15), 8 T) at offset c - 8 T + 120, and W_T (the inverted diagonal tile, row r - 8 T) in the
   // last 8 slots. A tile row is one contiguous 8 KB block: the back substitution fetches it with ONE bulk copy.
-  double *__restrict__ L = L_all + (size_t)side * Mp * 128;
-  auto Lg = [&](int rl, int cl) { return (size_t)rl * 128 + (cl - 8 * (rl >> 3) + 120); };
+  double *__restrict__ L = L_all + (size_t)side * Mp * kLs;
   double *z = dsm;                         // [Mp]   right-hand side -> forward solution -> solution
   double *dd = z + Mp;                     // [Mp]   damping ep + lm * S_rr, added when a diagonal tile is factored
   double *Psm = dd + Mp;                   // [2][16][64] panel tiles L_{J+i,J}, i = 1..15, operand layout, by column parity
@@ -124,13 +156,12 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
   double *Dnsm = zJ + 2 * 8;               // [2][64]  -D_{J+1} without column J's update, C layout [g][c] (diagonal 0 -> factor warp)
   double *Fsm = Dnsm + 2 * 64;             // [64]     factor warp: L_{J+1,J} in operand layout
   double *Hsm = Fsm + 64;                  // [64]     twist hand-over: -D_{c1} back from the factor warp, C layout
-  double *Lst = Hsm + 64;                  // [kBackStages][8][128] back-substitution stages
+  double *Lst = Psm;                       // [R][8][128] back-substitution stages: OVERLAY everything from Psm on (dead by then)
   double *xsol = dd;                       // solution of the back substitution (dd is dead then)
   __shared__ int s_fail, s_nan, s_abort;
   __shared__ volatile int s_colfail[2];      // the failure flag of the column of each parity (the factor warp runs one column ahead)
-  __shared__ __align__(8) unsigned long long s_mbar[kBackStages];
-  constexpr int kIssueThread = 160;        // lane 0 of tile warp 5: issues the stage copies
-  int bs_it = 0;
+  __shared__ __align__(8) unsigned long long s_mb[48];          // back substitution: full [0,16), xrdy [16,32), fdone [32,48)
+  unsigned long long *const s_full = s_mb, *const s_xrdy = s_mb + 16, *const s_fdone = s_mb + 32;
   // ---- streaming mode (feed.flags != nullptr), see ba_internal.h SolveFeed ----
   __shared__ volatile int s_cursor, s_giveup;
   int wcur = 0, fprobe = 0;
@@ -168,14 +199,16 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
   if (side) trace = nullptr;
   if (phase && tau == 0) phase[0] = clock64();
 
-  if (tau == 0) {
-    for (int k = 0; k < kBackStages; ++k)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_mbar[k])) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-
   for (int attempt = 0; attempt < 2; ++attempt) {
     const double lm = attempt == 0 ? 1e-4 : 1e-3;
+    if (tau == 0) {                                                // the back substitution's step numbers start at 0 in every attempt
+      for (int k = 0; k < 48; ++k) {
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(&s_mb[k]);
+        if (attempt) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(k >= 32 ? 3 : 1) : "memory");
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     auto Aval = [&](int rl, int cl) -> double {                  // local coordinates (reversed on side 1)
       if (cl > rl) return 0.0;
       const int r = side ? Mp - 1 - cl : rl, c = side ? Mp - 1 - rl : cl;   // global, r >= c
@@ -413,15 +446,15 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
             if (J + d < NTloc) {                                   // tiles below this side's matrix are all zero
               const int r = 8 * (J + d) + g;
               if (q == 0 && d > 2) z[r] -= part[k];
-              double *lp = L + (size_t)r * 128 + (2 * q - 8 * d + 120);   // L(r, 8J + 2q): even offset, one 16-byte store
+              double *lp = L + (size_t)r * kLs + (2 * q - 8 * d + 120);   // L(r, 8J + 2q): even offset, one 16-byte store
               const int dl = 8 * d + g - 2 * q;
               if (dl <= bw) *reinterpret_cast<double2 *>(lp) = make_double2(p0[k], p1[k]);
               else if (dl - 1 <= bw) lp[1] = p1[k];
             }
           }
           if (pw == kNP - 1) {
-            L[(size_t)(8 * J + (lane >> 3)) * 128 + 120 + (lane & 7)] = -Wsm[64 * p + op_idx(lane >> 3, lane & 7)];
-            L[(size_t)(8 * J + 4 + (lane >> 3)) * 128 + 120 + (lane & 7)] = -Wsm[64 * p + op_idx(4 + (lane >> 3), lane & 7)];
+            L[(size_t)(8 * J + (lane >> 3)) * kLs + 120 + (lane & 7)] = -Wsm[64 * p + op_idx(lane >> 3, lane & 7)];
+            L[(size_t)(8 * J + 4 + (lane >> 3)) * kLs + 120 + (lane & 7)] = -Wsm[64 * p + op_idx(4 + (lane >> 3), lane & 7)];
           }
         }
       }
@@ -692,24 +725,36 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
     const int ncols = (twist && side == 1) ? c1 : NTloc;            // tile columns of L (and W_J) this side owns
 
     // ---- backward substitution L^T x = z by tile rows, descending, in local coordinates ----
-    auto stage_issue = [&](int J, int it) {
-      const unsigned mb = (unsigned)__cvta_generic_to_shared(&s_mbar[it % kBackStages]);
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(Lst + (size_t)(it % kBackStages) * (8 * 128));
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(8 * 128 * 8) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(dst), "l"(L + (size_t)J * (8 * 128)), "r"(8 * 128 * 8), "r"(mb) : "memory");
-    };
-    auto stage_wait = [&](int it) {
-      const unsigned mb = (unsigned)__cvta_generic_to_shared(&s_mbar[it % kBackStages]);
-      const unsigned par = (unsigned)(it / kBackStages) & 1u;
+    // One CHAIN warp (the factor warp: alone on scheduler 0 now) carries the only dependent sequence,
+    //       x_J = W_J^T (z_J - sum_{d=1..15} L_{J+d,J}^T x_{J+d}),
+    // in registers — no CTA barrier, no shuffle per tile row. It keeps the NEAR field d = 1..4 itself (x_{J+1} is added
+    // to the sums of rows J .. J-3 as soon as it exists); three HELPER warps subtract the FAR field d = 5..15 from z
+    // five or more steps before the chain reads the row (a thread owns a row while d runs 15 -> 5: one store, no
+    // read-modify-write races); one LOADER thread keeps R tile rows of the stage-format factor in flight (bulk copies).
+    // Hand-shakes are mbarrier rings indexed by the step number n = Jhi - J: full (row landed), xrdy (x_J published),
+    // fdone (far field of x_J applied).
+    const int R = 1 << rlog, Rm = R - 1, Jhi = NTloc - 1;
+    auto mba = [&](unsigned long long *b) { return (unsigned)__cvta_generic_to_shared(b); };
+    auto mb_wait = [&](unsigned mb, unsigned par) {
       unsigned done = 0;
       while (!done) {
         asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
                      : "=r"(done) : "r"(mb), "r"(par) : "memory");
       }
     };
-    asm volatile("fence.proxy.async;" ::: "memory");                // this CTA's stores to L -> visible to the bulk copies
-    __threadfence_block();
+    auto full_mb = [&](int n) { return mba(&s_full[n & Rm]); };
+    auto ring_par = [&](int n) { return (unsigned)(n >> 4) & 1u; };
+    // one bulk copy per tile row (8 rows x kLs doubles, contiguous in global memory: the padding travels with the rows;
+    // eight copies of one row each cost the issuing thread ~60 cycles apiece and throttle the chain, tools/microbench_chain2.cu)
+    auto stage_issue = [&](int J, int n) {
+      const unsigned mb = full_mb(n);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(Lst) + (unsigned)(n & Rm) * (unsigned)kStSlot;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(kStSlot) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(L + (size_t)J * (8 * kLs)), "r"(kStSlot), "r"(mb) : "memory");
+    };
+    asm volatile("fence.proxy.async;" ::: "memory");                // this CTA's stores to L (and to the shared memory the
+    __threadfence_block();                                          // stages overlay) -> visible to the bulk copies
     bool anybad = bad;
     if (twist && side == 1) {                                      // wait for x_mid
       cluster_sync();
@@ -722,52 +767,158 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
     bool synced2 = !(twist && side == 0);                          // side 0 owes the cluster one barrier (x_mid hand-over)
     if (!anybad) {
       __syncthreads();
-      const int it0 = bs_it;
-      int issued = 0, consumed = 0;
-      if (tau == kIssueThread) {
-        for (int k = 0; k < kBackStages - 1 && NTloc - 1 - k >= 0; ++k) stage_issue(NTloc - 1 - k, it0 + k);
-      }
-      issued = min(kBackStages - 1, NTloc);
-      for (int J = NTloc - 1; J >= 0; --J) {
-        if (!synced2 && J == c1 - 1) {                             // middle solved: publish it, then carry on downwards
-          __syncthreads();
-          for (int i = tau; i < 128; i += kThreadsDg) XD[16384 + 128 + i] = xsol[8 * c1 + i];
-          if (tau == 0) gf[0] = 0;
-          cluster_sync();
-          synced2 = true;
-          if (gf[1] != 0) { anybad = true; break; }
-        }
-        const int it = it0 + (NTloc - 1 - J);
-        __syncthreads();
-        if (J - (kBackStages - 1) >= 0) {
-          if (tau == kIssueThread) stage_issue(J - (kBackStages - 1), it + kBackStages - 1);
-          ++issued;
-        }
-        if (tau < 160) stage_wait(it);
-        ++consumed;
-        const double *st = Lst + (size_t)(it % kBackStages) * (8 * 128);
-        if (tau < 8 && J < ncols) {
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int k = 0; k < 8; k += 2) {
-            if (k >= tau) s0 = fma(st[k * 128 + 120 + tau], z[8 * J + k], s0);
-            if (k + 1 >= tau) s1 = fma(st[(k + 1) * 128 + 120 + tau], z[8 * J + k + 1], s1);
+      constexpr int it0 = 0;
+      const bool mid_out = !synced2;                               // side 0 of a twisted solve publishes the middle
+      if (mid_out && !is_factor) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // the chain warp arrives when x_mid is out
+      if (is_factor) {
+        // =================== chain warp ===================
+        // A lone warp issues an instruction every ~6 cycles here, so the step is written for instruction count. Every
+        // 8x8 product is a DMMA pair with the vector as the A operand (all eight rows equal) and the tile as B; with
+        // the tile's rows fetched in the order 0,2,4,6 | 1,3,5,7 the C fragment a lane gets back (elements 2q, 2q+1)
+        // IS the A operand of the next product: no shuffle, no layout change anywhere on the chain. The step is
+        // unrolled over the ring position k = n & 15, so every shared address is a base register + an immediate.
+        // Near field as a register pipeline: a0 / a1 / a2 hold the sums of rows J-1 / J-2 / J-3.
+        auto chain = [&](auto rlc) {
+          constexpr int RL = decltype(rlc)::value, RM = (1 << RL) - 1;
+          const unsigned mbb = (unsigned)__cvta_generic_to_shared(s_mb);
+          const unsigned stg = (unsigned)__cvta_generic_to_shared(Lst) + (unsigned)(2 * q * kStRow + g * 8);
+          unsigned zq = (unsigned)__cvta_generic_to_shared(z) + (unsigned)(8 * Jhi + 2 * q) * 8u;   // z pair of the round's first row
+          unsigned xq = (unsigned)__cvta_generic_to_shared(xsol) + (unsigned)(8 * Jhi + 2 * q) * 8u;
+          unsigned parR = 0;                                       // parity of the round: (n >> 4) & 1
+          bool later = false;                                      // round > 0
+          int Jr = Jhi;
+          double x0 = 0.0, x1 = 0.0, a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+          double b00 = 0.0, b01 = 0.0, b10 = 0.0, b11 = 0.0, b20 = 0.0, b21 = 0.0, w0, w1;
+          long long w_far = 0, w_row = 0;
+          mbar_wait_o<0>(mbb, 0);
+          w0 = lds64o<120 * 8>(stg); w1 = lds64o<120 * 8 + kStRow>(stg);
+          // CK: the checked form (first round: rows without a far field yet, side 1's given rows, the hand-over of the
+          // middle; last round: the end of the matrix). Rounds in between run the same step without any of the tests.
+          auto step = [&](auto kc, auto ckc) -> bool {
+            constexpr int k = decltype(kc)::value, k1 = (k + 1) & 15, kf = (k - kNear - 1) & 15;
+            constexpr bool CK = decltype(ckc)::value;
+            constexpr int so = (k & RM) * kStSlot, so1 = (k1 & RM) * kStSlot;   // stage of row J, of row J - 1
+            const int J = Jr - k;
+            const bool nxt = !CK || J > 0, far = !CK || k >= kNear + 1 || later;
+            // parity of the row ring: sixteen stages turn once per round, eight or four several times per round
+            const unsigned pf1 = RL == 4 ? (k == 15 ? parR ^ 1u : parR) : (unsigned)((k1 >> RL) & 1);
+            const unsigned pfd = k >= kNear + 1 ? parR : parR ^ 1u;
+            unsigned fl = 1, fd = 1;                               // probes first: their answers are back when they are needed
+            if (nxt) fl = mbar_test_o<8 * (k1 & RM)>(mbb, pf1);
+            if (far) fd = mbar_test_o<8 * (32 + kf)>(mbb, pfd);
+            double t0, t1, e0, e1;
+            dmma884(e0, e1, x0, b00, a00, a01); dmma884(t0, t1, x1, b01, e0, e1);       // row J: near field complete
+            dmma884(e0, e1, x0, b10, a10, a11); dmma884(a00, a01, x1, b11, e0, e1);     // row J - 1
+            if (!(fd & fl)) {
+              const long long w0c = phase ? clock64() : 0;
+              if (far) mbar_wait_o<8 * (32 + kf)>(mbb, pfd);
+              const long long w1c = phase ? clock64() : 0;
+              if (nxt) mbar_wait_o<8 * (k1 & RM)>(mbb, pf1);
+              if (phase) { w_far += w1c - w0c; w_row += clock64() - w1c; }
+            }
+            const double2 zz = lds128o<-64 * k>(zq);
+            t0 = zz.x - t0; t1 = zz.y - t1;
+            double xn0, xn1;
+            dmma884(e0, e1, t0, w0, 0.0, 0.0); dmma884(xn0, xn1, t1, w1, e0, e1);       // x_J = W_J^T t
+            dmma884(e0, e1, x0, b20, 0.0, 0.0); dmma884(a10, a11, x1, b21, e0, e1);     // row J - 2
+            if (nxt) {                               // next step's operands: W of row J - 1, near tiles of row J
+              w0 = lds64o<so1 + 120 * 8>(stg); w1 = lds64o<so1 + 120 * 8 + kStRow>(stg);
+              b00 = lds64o<so + 112 * 8>(stg); b01 = lds64o<so + 112 * 8 + kStRow>(stg);
+              b10 = lds64o<so + 104 * 8>(stg); b11 = lds64o<so + 104 * 8 + kStRow>(stg);
+              b20 = lds64o<so + 96 * 8>(stg); b21 = lds64o<so + 96 * 8 + kStRow>(stg);
+            }
+            if (CK && J >= ncols) { const double2 xg = lds128o<-64 * k>(xq); xn0 = xg.x; xn1 = xg.y; }   // given (side 1: the middle)
+            else if (g == 0) sts128o<-64 * k>(xq, xn0, xn1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_o<8 * (16 + k)>(mbb);
+            x0 = xn0; x1 = xn1;
+            if (CK && mid_out && J == c1) {                        // middle solved: publish it, then carry on downwards
+              for (int kk = lane; kk < 128; kk += 32) XD[16384 + 128 + kk] = xsol[8 * c1 + kk];
+              if (lane == 0) gf[0] = 0;
+              asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            }
+            return CK && J == 0;
+          };
+#define BA_ROUND(CKV)                                                                                  \
+          if (step(std::integral_constant<int, 0>{}, std::integral_constant<bool, CKV>{})) break;      \
+          if (step(std::integral_constant<int, 1>{}, std::integral_constant<bool, CKV>{})) break;      \
+          if (step(std::integral_constant<int, 2>{}, std::integral_constant<bool, CKV>{})) break;      \
+          if (step(std::integral_constant<int, 3>{}, std::integral_constant<bool, CKV>{})) break;      \
+          if (step(std::integral_constant<int, 4>{}, std::integral_constant<bool, CKV>{})) break;      \
+          if (step(std::integral_constant<int, 5>{}, std::integral_constant<bool, CKV>{})) break;      \
+          if (step(std::integral_constant<int, 6>{}, std::integral_constant<bool, CKV>{})) break;      \
+          if (step(std::integral_constant<int, 7>{}, std::integral_constant<bool, CKV>{})) break;      \
+          if (step(std::integral_constant<int, 8>{}, std::integral_constant<bool, CKV>{})) break;      \
+          if (step(std::integral_constant<int, 9>{}, std::integral_constant<bool, CKV>{})) break;      \
+          if (step(std::integral_constant<int, 10>{}, std::integral_constant<bool, CKV>{})) break;     \
+          if (step(std::integral_constant<int, 11>{}, std::integral_constant<bool, CKV>{})) break;     \
+          if (step(std::integral_constant<int, 12>{}, std::integral_constant<bool, CKV>{})) break;     \
+          if (step(std::integral_constant<int, 13>{}, std::integral_constant<bool, CKV>{})) break;     \
+          if (step(std::integral_constant<int, 14>{}, std::integral_constant<bool, CKV>{})) break;     \
+          if (step(std::integral_constant<int, 15>{}, std::integral_constant<bool, CKV>{})) break;
+          for (;;) {
+            if (later && Jr >= 16) { BA_ROUND(false) }             // rows Jr .. Jr - 15 > 0, all with a far field
+            else { BA_ROUND(true) }
+            Jr -= 16; zq -= 1024u; xq -= 1024u; parR ^= 1u; later = true;
           }
-          xsol[8 * J + tau] = s0 + s1;
-        }
-        if (tau < 160) bar_sync(kBarX, 160);
-        if (tau >= 32 && tau < 32 + 120) {
-          const int xcol = tau - 32, c = 8 * (J - 15) + xcol;
-          if (c >= 0) {
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-            for (int gg = 0; gg < 8; gg += 2) { s0 += st[gg * 128 + xcol] * xsol[8 * J + gg]; s1 += st[(gg + 1) * 128 + xcol] * xsol[8 * J + gg + 1]; }
-            z[c] -= s0 + s1;
+#undef BA_ROUND
+          if (phase && lane == 0) { phase[4] = w_far; phase[5] = w_row; }
+        };
+        if (rlog == 4) chain(std::integral_constant<int, 4>{});
+        else if (rlog == 3) chain(std::integral_constant<int, 3>{});
+        else chain(std::integral_constant<int, 2>{});
+      } else if (tau < 96) {
+        // =================== helper warps: far field d = kNear + 1 .. 15 (twelve tiles x eight rows = 96 threads) ========
+        // x_J published implies row J of the factor has landed (the chain warp waited for it first). All addresses
+        // advance incrementally: the warps must keep up with the chain warp.
+        constexpr int kFar = 15 - kNear;                           // tiles of the far field = rows in flight per thread cycle
+        const int sI = tau >> 3, i = tau & 7;
+        int m = ((sI - Jhi + 15) % kFar + kFar) % kFar;            // row J - 15 + m is this thread's, d = 15 - m
+        const unsigned mbx = (unsigned)__cvta_generic_to_shared(s_mb) + 128u;   // xrdy ring (fdone: + 128)
+        const unsigned st0 = (unsigned)__cvta_generic_to_shared(Lst) + (unsigned)i * 8u;
+        unsigned xa = (unsigned)__cvta_generic_to_shared(xsol) + (unsigned)(8 * Jhi) * 8u;
+        unsigned slot = 0, ring = 0, par = 0;
+        double facc = 0.0;
+        long long w_x = 0;
+        for (int J = Jhi; J >= 0; --J) {
+          const int d = 15 - m;
+          const unsigned st = st0 + slot * (unsigned)kStSlot + (unsigned)(120 - 8 * d) * 8u;
+          { const long long t0 = phase ? clock64() : 0; mbar_wait_o<0>(mbx + ring * 8u, par); if (phase) w_x += clock64() - t0; }
+          const double2 xa0 = lds128o<0>(xa), xb0 = lds128o<16>(xa), xc0 = lds128o<32>(xa), xd0 = lds128o<48>(xa);
+          const double h0 = lds64o<0>(st), h1 = lds64o<kStRow>(st), h2 = lds64o<2 * kStRow>(st), h3 = lds64o<3 * kStRow>(st);
+          const double h4 = lds64o<4 * kStRow>(st), h5 = lds64o<5 * kStRow>(st), h6 = lds64o<6 * kStRow>(st), h7 = lds64o<7 * kStRow>(st);
+          const double c0 = fma(h1, xa0.y, h0 * xa0.x), c1s = fma(h3, xb0.y, h2 * xb0.x);
+          const double c2 = fma(h5, xc0.y, h4 * xc0.x), c3 = fma(h7, xd0.y, h6 * xd0.x);
+          facc += (c0 + c1s) + (c2 + c3);
+          if (d == kNear + 1) {
+            const int r = J - (kNear + 1);
+            if (r >= 0) z[8 * r + i] -= facc;
+            facc = 0.0;
           }
+          m = m == kFar - 1 ? 0 : m + 1;
+          __syncwarp();
+          if (lane == 0) mbar_arrive_o<128>(mbx + ring * 8u);
+          xa -= 64u;
+          slot = (slot + 1) & (unsigned)Rm;
+          ring = (ring + 1) & 15u;
+          par ^= (ring == 0);
+        }
+        if (phase && tau == 0) phase[7] = w_x;
+      } else if (tau == 96) {
+        // =================== loader ===================
+        for (int k = 0; k < R && Jhi - k >= 0; ++k) stage_issue(Jhi - k, it0 + k);
+        for (int J = Jhi - R; J >= 0; --J) {
+          const int n = it0 + (Jhi - J);                           // the slot held row J + R: the helpers are done with it
+          mb_wait(mba(&s_fdone[(n - R) & 15]), ring_par(n - R));   // after x_{J+R}, the chain after step J + R - 1
+          mb_wait(mba(&s_xrdy[(n - R + 1) & 15]), ring_par(n - R + 1));
+          stage_issue(J, n);
         }
       }
-      if (tau < 160) for (; consumed < issued; ++consumed) stage_wait(it0 + consumed);
-      bs_it = it0 + issued;
+      __syncthreads();                                             // idle warps block HERE (in hardware), not in the cluster wait below:
+      if (mid_out) {                                               // that one polls, and two of them share the chain warp's scheduler
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        synced2 = true;
+      }
     }
     if (!synced2) {
       if (tau == 0) gf[0] = 1;
@@ -802,19 +953,28 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
   if (phase && tau == 0) phase[3] = clock64();
 }
 
+// shared memory: z, dd (alive to the end) + the larger of the factorisation's buffers and the R back-substitution stages
+// that overlay them; R = 16, 8 or 4 tile rows, whatever fits (cfg3: 16, 1024 key frames: 16)
+static size_t diag_fixed_bytes() { return ((size_t)4 * 16 * 64 + 8 * kPs + 2 * 64 + 2 * 8 + 4 * 64) * sizeof(double); }
+static int diag_stage_log2(int M) {
+  const size_t Mp = ((size_t)(M + 7) / 8) * 8;
+  for (int lg = 4; lg > 2; --lg)
+    if (2 * Mp * sizeof(double) + ((size_t)kStSlot << lg) <= 227 * 1024 - 1024) return lg;
+  return 2;
+}
 size_t solve_diag_smem_bytes(int M) {
-  const int Mp = ((M + 7) / 8) * 8;
-  return ((size_t)2 * Mp + 4 * 16 * 64 + 8 * kPs + 2 * 64 + 2 * 8 + 4 * 64 + kBackStages * (8 * 128)) * sizeof(double);
+  const size_t Mp = ((size_t)(M + 7) / 8) * 8;
+  return 2 * Mp * sizeof(double) + std::max(diag_fixed_bytes(), (size_t)kStSlot << diag_stage_log2(M));
 }
 
 int launch_solve_band_diag(const CallView &cv, int allow_retry, double *scratch, const SolveFeed &feed, cudaStream_t s) {
   const size_t Mp = ((size_t)(cv.M + 7) / 8) * 8;
   const int nt = (int)(Mp / 8);
-  double *L_all = scratch, *XD = L_all + 2 * Mp * 128;
+  double *L_all = scratch, *XD = L_all + 2 * Mp * kLs;
   {                                     // never-written slots of L must read as zero: clear when the shape changes
     const long long key = ((long long)cv.M << 20) | cv.bw;
     if (feed.shape_key && *feed.shape_key != key) {
-      BA_CUDA(cudaMemsetAsync(L_all, 0, 2 * Mp * 128 * sizeof(double), s));
+      BA_CUDA(cudaMemsetAsync(L_all, 0, 2 * Mp * kLs * sizeof(double), s));
       *feed.shape_key = key;
     }
   }
@@ -833,13 +993,13 @@ int launch_solve_band_diag(const CallView &cv, int allow_retry, double *scratch,
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  BA_CUDA(cudaLaunchKernelEx(&cfg, k_solve_band_diag, cv, allow_retry, L_all, XD, gfl, twist, feed.trace, feed));
+  BA_CUDA(cudaLaunchKernelEx(&cfg, k_solve_band_diag, cv, allow_retry, L_all, XD, gfl, twist, feed.trace, feed, diag_stage_log2(cv.M)));
   BA_LAUNCH_CHECK();
   return BA_OK;
 }
 
 int solve_diag_prepare_device() {
-  return cudaFuncSetAttribute(k_solve_band_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) == cudaSuccess ? BA_OK : BA_ERR_CUDA;
+  return cudaFuncSetAttribute(k_solve_band_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) == cudaSuccess ? BA_OK : BA_ERR_CUDA;
 }
 
 }  // namespace ba

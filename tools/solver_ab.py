@@ -37,6 +37,8 @@ for sv in solvers:
         plan = Plan(t["ii"], t["jj"], t["kk"], N, NM)
         plan.set_option("solver", sv)
         plan.set_option("stream", stream)
+        import os
+        if os.environ.get("BA_EXP"): plan.set_option("spin_cap", int(os.environ["BA_EXP"]))
         n = plan.info.n_total - prob.fixedp
         plan.enable_timing(True)
         acc = {}
@@ -90,6 +92,6 @@ for sv in solvers:
                 print(f"   trace: tiles {nt} twist {int(twist)} | tile warp 0: top {d[0]:.0f} waitW {d[1]:.0f} P {d[2]:.0f} waitP {d[3]:.0f} "
                       f"U {d[4]:.0f} tail {d[5]:.0f} | factor warp: waitD {d[6]:.0f} A {d[7]:.0f} tail {d[8]:.0f} | step {step:.0f} cycles")
             for sd in range(2 if twist else 1):
-                ph = tr[16 * 4096 + sd * 8: 16 * 4096 + sd * 8 + 4]
-                print(f"   side {sd}: factor+forward {ph[1] - ph[0]}  back-substitution {ph[2] - ph[1]}  tail {ph[3] - ph[2]} cycles")
+                ph = tr[16 * 4096 + sd * 8: 16 * 4096 + sd * 8 + 8]
+                print(f"   side {sd}: factor+forward {ph[1] - ph[0]}  back-substitution {ph[2] - ph[1]}  tail {ph[3] - ph[2]} cycles | chain warp waited {ph[4]} for the far field, {ph[5]} for rows; helper warp 0 waited {ph[7]} for x")
         del plan
