@@ -303,6 +303,8 @@ struct HostPipe {
   unsigned long long seq = 0;
   unsigned pre_mask = 0;         // inputs of call `seq` that ba_prefetch_host_async has already put on the upload stream
   bool pre_waited = false;       // ... which has waited for the slot's previous user then
+  const void *out_ptr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // host arrays the call of each slot downloads into (poses, patches)
+  size_t out_len[2][2] = {{0, 0}, {0, 0}};
 };
 enum { PRE_MONO = 1, PRE_INTR = 2, PRE_TG = 4, PRE_W = 8, PRE_LAM = 16 };
 
@@ -417,6 +419,23 @@ extern "C" int ba_stage_host_async(BaPlan *pl, const BaProblem *ph, BaProblem *p
 #define H2D(field, off, bytes, bit)                                                                     \
   do { if (!(pre & (bit))) BA_CUDA(cudaMemcpyAsync(d + (off), ph->field, (bytes), cudaMemcpyHostToDevice, hp->h2d)); \
        pd.field = (const float *)(d + (off)); } while (0)
+  // Host-buffer hazard: an input array that a call still in flight downloads INTO (iteration k+1 starting from the host
+  // results of iteration k, main/batrack.py:869-884) is uploaded only after that download — ordered on the device, so a
+  // caller may enqueue dependent steps back to back without waiting on the host in between.
+  for (int k = 0; k < 2; ++k)
+    for (int a = 0; a < 2; ++a) {
+      const char *o = static_cast<const char *>(hp->out_ptr[k][a]);
+      if (!o) continue;
+      auto overlaps = [&](const void *in, size_t len) {
+        const char *i0 = static_cast<const char *>(in);
+        return in && i0 < o + hp->out_len[k][a] && o < i0 + len;
+      };
+      if (overlaps(ph->poses, 7 * N * f) || overlaps(ph->patches, 3 * NM * f) || overlaps(ph->monodisp, NM * f) ||
+          overlaps(ph->intrinsics, 4 * N * f) || overlaps(ph->targets, 2 * E * f) || overlaps(ph->weights, 2 * E * f)) {
+        BA_CUDA(cudaStreamWaitEvent(hp->h2d, hp->out_done[k], 0));
+        break;
+      }
+    }
   H2D(poses, o_pose, 7 * N * f, 0);
   H2D(patches, o_pat, 3 * NM * f, 0);
   if (ph->monodisp) H2D(monodisp, o_mono, NM * f, PRE_MONO);
@@ -446,6 +465,8 @@ extern "C" int ba_unstage_host_async(BaPlan *pl, const BaProblem *ph, const BaPr
   BA_CUDA(cudaMemcpyAsync(ph->poses_out, pd->poses_out, 7 * N * f, cudaMemcpyDeviceToHost, hp->d2h));
   BA_CUDA(cudaMemcpyAsync(ph->patches_out, pd->patches_out, 3 * NM * f, cudaMemcpyDeviceToHost, hp->d2h));
   BA_CUDA(cudaEventRecord(hp->out_done[slot], hp->d2h));
+  hp->out_ptr[slot][0] = ph->poses_out; hp->out_len[slot][0] = 7 * N * f;
+  hp->out_ptr[slot][1] = ph->patches_out; hp->out_len[slot][1] = 3 * NM * f;
   hp->seq++;
   return BA_OK;
 }

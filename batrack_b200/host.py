@@ -35,7 +35,9 @@ class HostBA:
     def submit(self, poses, patches, patches_monodisp, intrinsics, targets_2d, weights, lmbda, bounds, poses_out,
                patches_out, ep=100.0, fixedp=1, structure_only=False, loss='trivial', alpha=0.5, group=None):
         """Enqueue one step on the current CUDA stream and return at once. Inputs must stay unchanged and outputs
-        are valid only after `sync()`. With `group` (keyframe-sharded graph) the step is staged, assembled,
+        are valid only after `sync()`. An input array that an earlier, still running step writes its results into
+        (iteration k+1 starting from the results of iteration k, main/batrack.py:869-884) is uploaded after that
+        download, ordered on the device: dependent steps can be submitted back to back without a `sync()` in between. With `group` (keyframe-sharded graph) the step is staged, assembled,
         all-reduced over the group and solved through ba_stage_host_async / ba_assemble / ba_solve_update /
         ba_unstage_host_async."""
         if loss not in _capi.LOSS_IDS:

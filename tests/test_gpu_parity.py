@@ -487,6 +487,25 @@ def test_host_buffer_pipeline_equals_device_call():
         G, p = BA_rgbd_droid(G, p, t["patches_monodisp"], t["intrinsics"], t["targets_2d"], None, ws[k].cuda(), ps.lmbda, t["ii"], t["jj"],
                              t["kk"], ps.bounds, ep=ps.ep, fixedp=ps.fixedp, structure_only=False, loss=ps.loss, alpha=ps.alpha, plan=plan)
         assert rel_err(chain[k][0].numpy(), G.data.cpu().numpy()) < 1e-5 and rel_err(chain[k][1].numpy(), p.cpu().numpy()) < 1e-5
+    # the same dependent chain enqueued back to back, no host wait in between: the library orders the upload of step k+1
+    # after the download of step k into the same host arrays (host-buffer hazard tracking, ba_stage_host_async); two
+    # output arrays used in turn, as a caller would
+    ring = [(torch.empty(1, N, 7).pin_memory(), torch.empty(1, NM, 3, 1, 1).pin_memory()) for _ in range(2)]
+    steps = 6
+    cur = (host["poses"], host["patches"])
+    for k in range(steps):
+        hba.submit(cur[0], cur[1], host["patches_monodisp"], host["intrinsics"], host["targets_2d"], ws[k % 4], ps.lmbda, ps.bounds,
+                   ring[k & 1][0], ring[k & 1][1], ep=ps.ep, fixedp=ps.fixedp, structure_only=False, loss=ps.loss, alpha=ps.alpha)
+        if k + 1 < steps:
+            hba.prefetch(host["patches_monodisp"], host["intrinsics"], host["targets_2d"], ws[(k + 1) % 4])
+        cur = ring[k & 1]
+    hba.sync()
+    G, p = SE3(t["poses"]), t["patches"]
+    for k in range(steps):
+        G, p = BA_rgbd_droid(G, p, t["patches_monodisp"], t["intrinsics"], t["targets_2d"], None, ws[k % 4].cuda(), ps.lmbda, t["ii"], t["jj"],
+                             t["kk"], ps.bounds, ep=ps.ep, fixedp=ps.fixedp, structure_only=False, loss=ps.loss, alpha=ps.alpha, plan=plan)
+    last = ring[(steps - 1) & 1]
+    assert rel_err(last[0].numpy(), G.data.cpu().numpy()) < 1e-5 and rel_err(last[1].numpy(), p.cpu().numpy()) < 1e-5
     with pytest.raises(RuntimeError):
         hba.submit(t["poses"], host["patches"], host["patches_monodisp"], host["intrinsics"], host["targets_2d"], ws[0],
                    ps.lmbda, ps.bounds, *outs[0])
