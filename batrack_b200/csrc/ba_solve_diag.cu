@@ -362,16 +362,16 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
             double l0, l1;
             dmma884(l0, l1, af.x, wb.x, 0.0, 0.0);
             dmma884(l0, l1, af.y, wb.y, l0, l1);                   // L_{J+1,J}, C layout
-            Fsm[g * 8 + oc0] = l0; Fsm[g * 8 + oc1] = l1;          // -> operand layout through shared memory
+            // L L^T sums over the columns of L in any order: with columns 0,2,4,6 in the first k-step and 1,3,5,7 in the
+            // second, the C fragment of [L] (elements 2q, 2q+1 of row g) is both the A and the B operand — no trip
+            // through shared memory
+            double n0 = Dnsm[64 * pn + g * 8 + 2 * q], n1 = Dnsm[64 * pn + g * 8 + 2 * q + 1];
+            dmma884(n0, n1, l0, l0, n0, n1);
+            dmma884(n0, n1, l1, l1, n0, n1);                       // -D_{J+1} with the update of column J
             double part = l0 * zJ[8 * p + 2 * q] + l1 * zJ[8 * p + 2 * q + 1];
             part += __shfl_xor_sync(0xffffffffu, part, 1);
             part += __shfl_xor_sync(0xffffffffu, part, 2);
             if (q == 0 && J + 1 < NTloc) z[8 * (J + 1) + g] -= part;   // z_{J+1} -= L zJ (the panel warps skip d = 1)
-            double n0 = Dnsm[64 * pn + g * 8 + 2 * q], n1 = Dnsm[64 * pn + g * 8 + 2 * q + 1];
-            __syncwarp();
-            const double2 f1 = *reinterpret_cast<const double2 *>(Fsm + 2 * lane);
-            dmma884(n0, n1, f1.x, f1.x, n0, n1);
-            dmma884(n0, n1, f1.y, f1.y, n0, n1);                   // -D_{J+1} with the update of column J
             if (J + 1 < je) {
               const double dmp = dd[8 * (J + 1) + g];
               Dsm[g * kPs + 2 * q] = (2 * q == g ? dmp : 0.0) - n0;
