@@ -37,8 +37,6 @@ for sv in solvers:
         plan = Plan(t["ii"], t["jj"], t["kk"], N, NM)
         plan.set_option("solver", sv)
         plan.set_option("stream", stream)
-        import os
-        if os.environ.get("BA_EXP"): plan.set_option("spin_cap", int(os.environ["BA_EXP"]))
         n = plan.info.n_total - prob.fixedp
         plan.enable_timing(True)
         acc = {}
