@@ -50,6 +50,7 @@ constexpr int kBarX = 8;                      // x_J of the back substitution
 constexpr int kBarZ = 9;                      // twist hand-over: z of the middle complete (tile warps)
 constexpr int kBarN = 10;                     // 10, 11: tile (J+1,J+1) without column J's update shipped (warp of diagonal 0 -> factor warp)
 constexpr int kCntP = 32 * (kNW + kNP), kCntA = 32 * (kNW + kNP + 1), kCntW = 32 * (kNP + 1);
+constexpr int kTwistShift = 60;               // side 0 eliminates 1/2 + 1/60 of the tile columns outside the middle
 constexpr int kLs = 132;                       // doubles per row of the stage-format factor in global memory (128 + 4 of padding)
 constexpr int kStRow = kLs * 8;                   // bytes between the rows of a staged tile row: rows 0,2,4,6 (1,3,5,7) of a tile
                                               // start 64 bytes apart modulo 128: a B-fragment load takes the minimum two wavefronts
@@ -143,7 +144,9 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
   const int M = cv.M, bw = cv.bw, ld = cv.ld, off = cv.off;
   const int NT8 = (M + 7) >> 3, Mp = NT8 * 8;
   const int side = twist ? (int)blockIdx.x : 0;
-  const int Jm0 = (NT8 - 16) / 2, Jm1 = NT8 - 16 - Jm0;
+  // side 1 (reversed coordinates: its two elements of a fragment sit in different rows of S) runs ~6 % slower per tile
+  // column than side 0; side 0 takes a few columns more so that both reach the hand-over together
+  const int Jm0 = min(NT8 - 16, (NT8 - 16) / 2 + (NT8 - 16) / kTwistShift), Jm1 = NT8 - 16 - Jm0;
   const int c1 = twist ? (side ? Jm1 : Jm0) : NT8;                  // end of this side's first segment
   const int NTloc = twist ? c1 + 16 : NT8;                          // tiles this side ever sees (local coordinates)
   // This side's factor in "stage format": 128 doubles per row; row r of tile row T = r / 8 holds L(r, c) for the 120

@@ -228,7 +228,11 @@ int ba_plan_last_timing(BaPlan *plan, float *ms_out /* host, BA_N_STAGES floats 
  * own upload stream, ba_step runs on `stream`, results return on the plan's download stream: the upload of
  * call k+1 and the download of call k-1 overlap the kernels of call k.
  *   ba_step_host_async  enqueue one step and return; host inputs must stay untouched until the step's upload has
- *                       run and the host outputs are valid only after ba_host_sync.
+ *                       run and the host outputs are valid only after ba_host_sync. Host-buffer hazards are tracked: an
+ *                       input array that one of the two calls still in flight downloads INTO (iteration k+1 starting
+ *                       from the poses / patches iteration k returns, main/batrack.py:869-884) is uploaded after that
+ *                       download, ordered on the device — dependent steps may be enqueued back to back, the host need
+ *                       not wait in between.
  *   ba_host_sync        order `stream` after the download of every step submitted so far; block != 0 also waits
  *                       on the host.
  *   ba_step_host        one synchronous step (= async + blocking sync).

@@ -19,9 +19,9 @@ tr = plan.read_trace()
 h = tr[:16 * 4096].reshape(4096, 16).astype(np.float64)
 ncol = 80
 base = h[10:ncol, 10]          # W_J published (factor warp, column J)
-names = {0: "tile0 top", 1: "tile0 after barP", 2: "tile0 first tile shipped (Dn)", 3: "tile0 end of U", 4: "panel0 top", 5: "panel0 after barA", 6: "panel0 after barW", 7: "panel0 arrive P", 8: "factor top", 9: "factor D loaded", 10: "factor W published", 11: "factor after barA", 12: "factor after barN (D_{J+1} here)", 13: "factor [L] done", 14: "factor [D] done", 15: "factor D_{J+1} stored"}
+names = {0: "tile0 top", 1: "tile0 after barP", 2: "tile0 first tile shipped (Dn)", 3: "tile0 end of U", 4: "panel0 top", 5: "panel0 after barA", 6: "panel0 after barW", 7: "panel0 arrive P", 8: "factor top", 9: "factor D loaded", 10: "factor W published"}
 print("offsets relative to 'factor W_J published' (column J), mean over columns; same-column stamps and next-column stamps")
-for k in range(16):
+for k in range(11):
     print(f"  col J   {names[k]:34s} {np.mean(h[10:ncol, k] - base):8.0f}")
-for k in range(16):
+for k in range(11):
     print(f"  col J+1 {names[k]:34s} {np.mean(h[11:ncol + 1, k] - base):8.0f}")
