@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbatrack_ba.so")
+# BATRACK_B200_LIB: another build of the same library (the sanitizer verification build, tools/racecheck_verify.sh)
+LIB_PATH = os.environ.get("BATRACK_B200_LIB") or os.path.join(_HERE, "libbatrack_ba.so")
 _lib = None
 
 STAGES = ("zero", "edge_pass", "track_q", "schur", "solve", "backsub", "pose_retr")   # BA_STAGE_*

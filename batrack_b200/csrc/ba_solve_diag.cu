@@ -55,6 +55,14 @@ constexpr int kLs = 132;                       // doubles per row of the stage-f
 constexpr int kStRow = kLs * 8;                   // bytes between the rows of a staged tile row: rows 0,2,4,6 (1,3,5,7) of a tile
                                               // start 64 bytes apart modulo 128: a B-fragment load takes the minimum two wavefronts
 constexpr int kStSlot = 8 * kStRow;           // one staged tile row
+// BA_VERIFY_SYNC (tools/racecheck_verify.sh): every thread that reads or writes behind one of the back substitution's
+// mbarriers arrives on it itself (the product build lets one lane arrive after a __syncwarp), and the helper warps wait
+// for the row's `full` barrier themselves — the form in which compute-sanitizer's racecheck can follow the protocol
+#ifdef BA_VERIFY_SYNC
+constexpr int kXrdyCount = 32, kFdoneCount = 96;
+#else
+constexpr int kXrdyCount = 1, kFdoneCount = 3;
+#endif
 constexpr int kNear = 3;                      // tile distances the chain warp of the back substitution keeps to itself
 constexpr int kPs = 12;                       // row stride (doubles) of the shared diagonal tile
 
@@ -212,7 +220,7 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
       for (int k = 0; k < 48; ++k) {
         const unsigned mb = (unsigned)__cvta_generic_to_shared(&s_mb[k]);
         if (attempt) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(k >= 32 ? 3 : 1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(k >= 32 ? kFdoneCount : (k >= 16 ? kXrdyCount : 1)) : "memory");
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -763,20 +771,26 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
     asm volatile("fence.proxy.async;" ::: "memory");                // this CTA's stores to L (and to the shared memory the
     __threadfence_block();                                          // stages overlay) -> visible to the bulk copies
     bool anybad = bad;
+    // x_mid travels through global memory behind a release / acquire flag (gf[3]: 1 = there, 2 = side 0 failed): side 0
+    // publishes it from inside its chain, and a split cluster barrier (arrive early, wait late) there turned out to hang
+    // under compute-sanitizer, which appears to block at the arrive
     if (twist && side == 1) {                                      // wait for x_mid
-      cluster_sync();
-      anybad = bad || gf[0] != 0 || gf[1] != 0;
+      if (tau == 0) {
+        int f = 0;
+        do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(gf + 3) : "memory"); if (!f) __nanosleep(64); } while (!f);
+      }
+      __syncthreads();
+      anybad = bad || __ldcg(gf + 3) != 1 || __ldcg(gf + 0) != 0 || __ldcg(gf + 1) != 0;
       if (!anybad) {
-        for (int i = tau; i < 128; i += kThreadsDg) xsol[8 * c1 + i] = XD[16384 + 128 + (Mp - 1 - (8 * c1 + i) - 8 * Jm0)];
+        for (int i = tau; i < 128; i += kThreadsDg) xsol[8 * c1 + i] = __ldcg(XD + 16384 + 128 + (Mp - 1 - (8 * c1 + i) - 8 * Jm0));
       }
       __syncthreads();
     }
-    bool synced2 = !(twist && side == 0);                          // side 0 owes the cluster one barrier (x_mid hand-over)
+    bool synced2 = !(twist && side == 0);                          // side 0 owes side 1 the flag (x_mid hand-over)
     if (!anybad) {
       __syncthreads();
       constexpr int it0 = 0;
       const bool mid_out = !synced2;                               // side 0 of a twisted solve publishes the middle
-      if (mid_out && !is_factor) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // the chain warp arrives when x_mid is out
       if (is_factor) {
         // =================== chain warp ===================
         // A lone warp issues an instruction every ~6 cycles here, so the step is written for instruction count. Every
@@ -836,13 +850,19 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
             }
             if (CK && J >= ncols) { const double2 xg = lds128o<-64 * k>(xq); xn0 = xg.x; xn1 = xg.y; }   // given (side 1: the middle)
             else if (g == 0) sts128o<-64 * k>(xq, xn0, xn1);
+#ifdef BA_VERIFY_SYNC
+            mbar_arrive_o<8 * (16 + k)>(mbb);
+#else
             __syncwarp();
             if (lane == 0) mbar_arrive_o<8 * (16 + k)>(mbb);
+#endif
             x0 = xn0; x1 = xn1;
             if (CK && mid_out && J == c1) {                        // middle solved: publish it, then carry on downwards
+              __syncwarp();                                        // (lanes 0-3 wrote x, every lane reads it)
               for (int kk = lane; kk < 128; kk += 32) XD[16384 + 128 + kk] = xsol[8 * c1 + kk];
-              if (lane == 0) gf[0] = 0;
-              asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+              __threadfence();
+              __syncwarp();
+              if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(gf + 3), "r"(1) : "memory");
             }
             return CK && J == 0;
           };
@@ -891,6 +911,9 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
           const int d = 15 - m;
           const unsigned st = st0 + slot * (unsigned)kStSlot + (unsigned)(120 - 8 * d) * 8u;
           { const long long t0 = phase ? clock64() : 0; mbar_wait_o<0>(mbx + ring * 8u, par); if (phase) w_x += clock64() - t0; }
+#ifdef BA_VERIFY_SYNC
+          mb_wait(full_mb(Jhi - J), (unsigned)((Jhi - J) >> rlog) & 1u);
+#endif
           const double2 xa0 = lds128o<0>(xa), xb0 = lds128o<16>(xa), xc0 = lds128o<32>(xa), xd0 = lds128o<48>(xa);
           const double h0 = lds64o<0>(st), h1 = lds64o<kStRow>(st), h2 = lds64o<2 * kStRow>(st), h3 = lds64o<3 * kStRow>(st);
           const double h4 = lds64o<4 * kStRow>(st), h5 = lds64o<5 * kStRow>(st), h6 = lds64o<6 * kStRow>(st), h7 = lds64o<7 * kStRow>(st);
@@ -903,8 +926,12 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
             facc = 0.0;
           }
           m = m == kFar - 1 ? 0 : m + 1;
+#ifdef BA_VERIFY_SYNC
+          mbar_arrive_o<128>(mbx + ring * 8u);
+#else
           __syncwarp();
           if (lane == 0) mbar_arrive_o<128>(mbx + ring * 8u);
+#endif
           xa -= 64u;
           slot = (slot + 1) & (unsigned)Rm;
           ring = (ring + 1) & 15u;
@@ -921,15 +948,15 @@ __global__ void __launch_bounds__(kHwThreadsDg, 1) k_solve_band_diag(CallView cv
           stage_issue(J, n);
         }
       }
-      __syncthreads();                                             // idle warps block HERE (in hardware), not in the cluster wait below:
-      if (mid_out) {                                               // that one polls, and two of them share the chain warp's scheduler
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-        synced2 = true;
-      }
+      __syncthreads();
+      if (mid_out) synced2 = true;
     }
-    if (!synced2) {
-      if (tau == 0) gf[0] = 1;
-      cluster_sync();
+    if (!synced2) {                                                // side 0 failed: tell side 1 (which waits for the flag)
+      if (tau == 0) {
+        gf[0] = 1;
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(gf + 3), "r"(2) : "memory");
+      }
       synced2 = true;
       anybad = true;
     }
