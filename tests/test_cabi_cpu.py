@@ -82,3 +82,19 @@ def test_synth_shards_partition_the_graph():
         assert np.array_equal(cat(k)[order], getattr(full, k)[forder])
     assert np.array_equal(cat("targets")[order], full.targets[forder])
     assert np.array_equal(parts[0].poses, full.poses) and np.array_equal(parts[1].patches, full.patches)
+
+
+def test_verification_build_exports_the_same_abi():
+    """tools/racecheck_verify.sh builds the band solver with -DBA_VERIFY_SYNC into libbatrack_ba_verify.so (the form
+    compute-sanitizer's racecheck can follow; selected with BATRACK_B200_LIB). When it is there it must export every
+    symbol the product library does."""
+    import ctypes
+    import os
+    import pytest
+    from batrack_b200 import _capi
+    path = os.path.join(os.path.dirname(_capi.__file__), "libbatrack_ba_verify.so")
+    if not os.path.exists(path):
+        pytest.skip("verification build not present (bash tools/racecheck_verify.sh build)")
+    lib = ctypes.CDLL(path)
+    for name in _capi.SYMBOLS:
+        assert hasattr(lib, name), name
