@@ -19,4 +19,6 @@ python tools/solver_ab.py cfg3 diag > gpurun_out/${R}_solver_cfg3.txt 2>&1
 python tools/solver_ab.py davis diag,tiles,window > gpurun_out/${R}_solver_davis.txt 2>&1
 python tools/solver_ab.py sintel tiles,window > gpurun_out/${R}_solver_sintel.txt 2>&1
 python tools/schur_trace.py cfg3 > gpurun_out/${R}_schur_trace.txt 2>&1
+python tools/solver_timeline.py > gpurun_out/${R}_solver_timeline.txt 2>&1
+python tools/sass_excerpt.py > gpurun_out/${R}_sass.txt 2>&1
 ls -la gpurun_out/ | tail -30
