@@ -1,6 +1,7 @@
 // ba_aux.cu — standalone SE3 forward ops (the lietorch_backends surface the BA caller touches,
 // main/backend/lietorch/src/lietorch.cpp:286-316, kernels lietorch_gpu.cu:21-283), reprojection
 // without Jacobians (projective_ops.py:54-70), and the host-buffer wrapper used for end-to-end timing.
+#include <cstdint>
 #include <cstring>
 
 #include "ba_internal.h"
@@ -424,10 +425,10 @@ extern "C" int ba_stage_host_async(BaPlan *pl, const BaProblem *ph, BaProblem *p
   // caller may enqueue dependent steps back to back without waiting on the host in between.
   for (int k = 0; k < 2; ++k)
     for (int a = 0; a < 2; ++a) {
-      const char *o = static_cast<const char *>(hp->out_ptr[k][a]);
+      const uintptr_t o = reinterpret_cast<uintptr_t>(hp->out_ptr[k][a]);
       if (!o) continue;
       auto overlaps = [&](const void *in, size_t len) {
-        const char *i0 = static_cast<const char *>(in);
+        const uintptr_t i0 = reinterpret_cast<uintptr_t>(in);
         return in && i0 < o + hp->out_len[k][a] && o < i0 + len;
       };
       if (overlaps(ph->poses, 7 * N * f) || overlaps(ph->patches, 3 * NM * f) || overlaps(ph->monodisp, NM * f) ||
